@@ -1,0 +1,115 @@
+"""Seeded synthetic inputs for the occupancy hot path.
+
+There is no nuScenes data (and no network) in this environment, so every test and the
+benchmark run on these fixtures.  Matrix conventions follow the reference's dataset
+class: `lidar2img = viewpad @ lidar2cam_rt.T` (datasets/nuscenes_occ.py:96-113) and
+`ego2lidar = inv(pseudo_lidar2ego)` (tools/ray_iou/ego_pose_extractor.py:24-28).
+"""
+import math
+
+import numpy as np
+import torch
+
+PC_RANGE = [-40.0, -40.0, -1.0, 40.0, 40.0, 5.4]
+
+# (yaw deg, focal, translation) for a nuScenes-like 6-camera rig
+_RIG = [(0.0, 1266.0, (1.7, 0.0, 1.5)), (-55.0, 1266.0, (1.5, -0.5, 1.5)), (55.0, 1266.0, (1.5, 0.5, 1.5)),
+        (180.0, 809.0, (0.0, 0.0, 1.5)), (110.0, 1266.0, (1.0, 0.5, 1.5)), (-110.0, 1266.0, (1.0, -0.5, 1.5))]
+
+# tools/ray_iou/ego_pose_extractor.py:24-28 (constant of the reference; lidar -> ego)
+PSEUDO_LIDAR2EGO = np.array([[0.0, 1.0, 0.0, 0.9858], [-1.0, 0.0, 0.0, 0.0], [0.0, 0.0, 1.0, 1.8402],
+                             [0.0, 0.0, 0.0, 1.0]])
+
+CFG_FULL = dict(bev_h=200, bev_w=200, embed_dims=256, num_heads=8, num_layers=4, num_points_in_pillar=8,
+                sca_points=8, num_levels=4, tsa_points=4, num_bev_queue=2, ffn_dim=512, pillar_h=16,
+                out_dim=32, num_classes=17, num_cams=6, pc_range=PC_RANGE,
+                img_shape=(928, 1600, 3), level_shapes=[(116, 200), (58, 100), (29, 50), (15, 25)])
+
+CFG_TOY = dict(CFG_FULL, bev_h=50, bev_w=50, num_layers=1, num_cams=1, img_shape=(256, 256, 3),
+               level_shapes=[(32, 32), (16, 16), (8, 8), (4, 4)])
+
+CFG_SMALL6 = dict(CFG_FULL, bev_h=40, bev_w=40, num_layers=2, img_shape=(928, 1600, 3),
+                  level_shapes=[(29, 50), (15, 25), (8, 13), (4, 7)])
+
+
+def make_cfg(base='full', **kw):
+    c = dict({'full': CFG_FULL, 'toy': CFG_TOY, 'small6': CFG_SMALL6}[base])
+    c.update(kw)
+    return c
+
+
+def camera_rig(num_cams=6, img_hw=(928, 1600)):
+    """-> (lidar2img (num_cams,4,4) float64, ego2lidar (4,4) float64)."""
+    R0 = np.array([[0.0, 0.0, 1.0], [-1.0, 0.0, 0.0], [0.0, -1.0, 0.0]])        # cam (z fwd, x right, y down) -> ego
+    lidar2ego = PSEUDO_LIDAR2EGO
+    ego2lidar = np.linalg.inv(lidar2ego)
+    out = []
+    sx = img_hw[1] / 1600.0
+    sy = img_hw[0] / 928.0
+    for yaw, f, t in _RIG[:num_cams]:
+        a = math.radians(yaw)
+        Rz = np.array([[math.cos(a), -math.sin(a), 0.0], [math.sin(a), math.cos(a), 0.0], [0.0, 0.0, 1.0]])
+        cam2ego = np.eye(4)
+        cam2ego[:3, :3] = Rz @ R0
+        cam2ego[:3, 3] = t
+        sensor2lidar = ego2lidar @ cam2ego
+        s2l_R, s2l_t = sensor2lidar[:3, :3], sensor2lidar[:3, 3]
+        lidar2cam_r = np.linalg.inv(s2l_R)
+        lidar2cam_t = s2l_t @ lidar2cam_r.T
+        rt = np.eye(4)
+        rt[:3, :3] = lidar2cam_r.T
+        rt[3, :3] = -lidar2cam_t
+        K = np.array([[f * sx, 0.0, 816.0 * sx], [0.0, f * sy, 491.0 * sy], [0.0, 0.0, 1.0]], dtype=np.float32)
+        viewpad = np.eye(4)
+        viewpad[:3, :3] = K
+        out.append(viewpad @ rt.T)
+    return np.stack(out), ego2lidar
+
+
+def make_img_metas(cfg, bs=1, can_bus_angle=None):
+    l2i, e2l = camera_rig(cfg['num_cams'], cfg['img_shape'][:2])
+    metas = []
+    for _ in range(bs):
+        m = dict(lidar2img=[l2i[i] for i in range(cfg['num_cams'])], ego2lidar=e2l,
+                 img_shape=[tuple(cfg['img_shape'])] * cfg['num_cams'])
+        if can_bus_angle is not None:
+            cb = np.zeros(18)
+            cb[-1] = can_bus_angle
+            m['can_bus'] = cb
+        metas.append(m)
+    return metas
+
+
+def make_feats(cfg, bs=1, seed=1, device='cpu', dtype=torch.float32):
+    """FPN-like multi-level camera features ~ N(0,1): list of (B, num_cams, C, h, w)."""
+    g = torch.Generator().manual_seed(seed)
+    feats = []
+    for (h, w) in cfg['level_shapes']:
+        feats.append(torch.randn(bs, cfg['num_cams'], cfg['embed_dims'], h, w, generator=g).to(device=device, dtype=dtype))
+    return feats
+
+
+def make_occ_scene(seed=4, size=(200, 200, 16), num_boxes=40):
+    """Synthetic GT semantics (X,Y,Z) uint8 + flow (X,Y,Z,2) fp32 (SURVEY 8d 'metric fixture')."""
+    rng = np.random.RandomState(seed)
+    X, Y, Z = size
+    sem = np.full(size, 16, np.uint8)
+    flow = np.zeros(size + (2,), np.float32)
+    sem[:, :, 0:2] = 10                                                            # ground slab
+    sem[: X // 10, :, 2:10] = 14                                                   # manmade wall
+    sem[:, : Y // 12, 2:7] = 15                                                    # vegetation wall
+    for _ in range(num_boxes):
+        c = rng.randint(0, 10)
+        sx, sy, sz = rng.randint(2, 12), rng.randint(2, 12), rng.randint(2, 6)
+        x0, y0 = rng.randint(0, X - sx), rng.randint(0, Y - sy)
+        sem[x0:x0 + sx, y0:y0 + sy, 2:2 + sz] = c
+        if c < 8:
+            flow[x0:x0 + sx, y0:y0 + sy, 2:2 + sz] = rng.uniform(-5, 5, 2).astype(np.float32)
+    return sem, flow
+
+
+def make_ray_origins(T=8, z=1.84):
+    """(1, T, 3) fp32 ego-frame origins along x in [-20, 20] (all pass ego_pose_extractor's |x|,|y| < 39)."""
+    xs = np.linspace(-20.0, 20.0, T)
+    o = np.stack([xs, np.zeros(T), np.full(T, z)], -1).astype(np.float32)
+    return o[None]
