@@ -1,0 +1,153 @@
+/* libocc_b200 -- C ABI of the B200-native camera->occupancy hot path.
+ *
+ * Every entry point takes plain pointers and sizes (no torch / C++ types) and returns 0 on success;
+ * on failure it returns non-zero and occb200_last_error() describes the problem (thread-local).
+ * "dev" pointers are CUDA device pointers on the current device; `stream` is a cudaStream_t passed
+ * as void* (NULL = default stream).  Calls are asynchronous on `stream` unless stated otherwise.
+ * Inputs are borrowed and never mutated; outputs are caller-allocated.
+ *
+ * Reference interfaces replaced (paths relative to the reference repository root):
+ *   [R1] mmcv._ext.ms_deform_attn_forward, bound at
+ *        projects/mmdet3d_plugin/bevformer/modules/multi_scale_deformable_attn_function.py:118-124
+ *        (ext loaded at encoder.py:24-25, spatial_cross_attention.py:27-28, temporal_self_attention.py:21-22)
+ *   [R2] BEVFormerOccHead.forward + get_occ, projects/mmdet3d_plugin/bevformer/dense_heads/bevformer_occ_head.py:99-160,198-216
+ *        -> TransformerOcc.forward (modules/transformer_occ.py:245-321) -> BEVFormerEncoder.forward (modules/encoder.py:153-239)
+ *   [R3] dvr.render_forward, tools/ray_iou/lib/dvr/dvr.cpp:39-48 / dvr.cu:329-388
+ *   [R4] ray_metrics.process_one_sample + calc_metrics, projects/mmdet3d_plugin/datasets/ray_metrics.py:89-197
+ */
+#ifndef OCC_B200_H_
+#define OCC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* occb200_last_error(void);
+/* "occ_b200 <ver> sm_100a" */
+const char* occb200_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * [R1] Multi-scale deformable attention, operator boundary (fp32, mmcv `_ext` argument meaning).
+ *   value          dev f32 [B, Nv, M, C]        contiguous
+ *   spatial_shapes dev i64 [L, 2] (h, w)        level_start_index dev i64 [L]
+ *   sampling_loc   dev f32 [B, Nq, M, L, P, 2]  (x, y) normalised to [0,1]
+ *   attn_weight    dev f32 [B, Nq, M, L, P]
+ *   out            dev f32 [B, Nq, M*C]
+ *   im2col_step is accepted for signature compatibility; mmcv asserts B % min(B, im2col_step) == 0
+ *   and so does this entry (error code 1).
+ */
+int occb200_ms_deform_attn_forward(const float* value, const int64_t* spatial_shapes,
+                                   const int64_t* level_start_index, const float* sampling_loc,
+                                   const float* attn_weight, int B, int Nv, int M, int C, int Nq, int L, int P,
+                                   int im2col_step, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * [R2] Frame engine: packs BEV queries, runs the BEVFormerEncoder layers (temporal self-attention,
+ * spatial cross-attention, FFN), the Conv3d voxel decoder and the occupancy / flow heads.
+ */
+typedef struct occb200_engine occb200_engine;
+
+typedef struct occb200_config {
+    int bev_h, bev_w;              /* BEV grid (200 x 200)                     bevformer_base_occ.py:41-42   */
+    int embed_dims, num_heads;     /* 256, 8 (only these are supported)                                      */
+    int num_layers;                /* encoder layers (4 shipped, 6 BEVFormer-base)          :101             */
+    int num_cams;                  /* <= 8                                                                   */
+    int num_levels;                /* 4                                                                      */
+    int level_h[4], level_w[4];    /* FPN level shapes                                                       */
+    int num_points_in_pillar;      /* D in {1,2,4,8}                                        :103             */
+    int sca_points, tsa_points;    /* 8, 4                                                  :118, default 4  */
+    int ffn_dim;                   /* 512                                                   :125             */
+    int pillar_h, out_dim;         /* 16, 32                                                :92, default     */
+    int num_classes;               /* 17                                                                     */
+    float pc_range[6];
+    int precision;                 /* 0 = fp32 storage + fp32 CUDA-core GEMMs (parity config),
+                                      1 = bf16 storage, fp32 accumulate (throughput config)                  */
+    int use_tensor_cores;          /* 1 = tcgen05 GEMM / conv kernels where available (precision 1 only)     */
+} occb200_config;
+
+int occb200_engine_create(const occb200_config* cfg, occb200_engine** out);
+void occb200_engine_destroy(occb200_engine* e);
+
+/* Load one parameter by its key in `pts_bbox_head.state_dict()` (e.g.
+ * "transformer.encoder.layers.0.attentions.1.output_proj.weight").  `data` is HOST fp32, `numel` its size.
+ * Unknown keys return error 3 (so a checkpoint/key-contract mismatch is loud).  Call _finalize afterwards. */
+int occb200_engine_load_param(occb200_engine* e, const char* key, const float* data, int64_t numel);
+/* Folds BatchNorm, concatenates the offset/weight projections, converts to the storage precision and
+ * checks that every parameter the configuration needs was loaded.  Synchronous. */
+int occb200_engine_finalize(occb200_engine* e);
+
+/* Camera geometry of the frame(s) to come: cam_mat HOST f32 [num_cams,16] = lidar2img[c] @ ego2lidar (fp32
+ * product, encoder.py:126), zs HOST f32 [D] = linspace(.5, Z-.5, D)/Z (encoder.py:66-67), image (h, w) =
+ * img_metas[0]['img_shape'][0][:2] (encoder.py:133-134). */
+int occb200_engine_set_cameras(occb200_engine* e, const float* cam_mat, const float* zs, int img_h, int img_w);
+
+/* One frame, DEVICE buffers.
+ *   feats[l]   dev f32 [num_cams, C, h_l, w_l]  (FPN outputs of one batch item, NCHW)
+ *   prev_bev   dev f32 [Nq, C] or NULL          (already rotated; NULL = the reference's only runtime mode)
+ * Outputs (any may be NULL to skip):
+ *   bev_embed  dev f32 [Nq, C]                   (= reference bev_embed permuted to (Nq, C))
+ *   occ_logits dev f32 [X, Y, Z, num_classes]    flow dev f32 [X, Y, Z, 2]
+ *   occ_cls_u8 dev u8  [X, Y, Z]                 occ_cls_i64 dev i64 [X, Y, Z]   (argmax, get_occ) */
+int occb200_engine_forward(occb200_engine* e, const float* const* feats, const float* prev_bev, float* bev_embed,
+                           float* occ_logits, float* flow, uint8_t* occ_cls_u8, int64_t* occ_cls_i64, void* stream);
+
+/* One frame, HOST buffers (pinned recommended): copies feats host->device, runs the frame, copies
+ * occ_cls (int64, the reference's LongTensor) / flow back and synchronises.  This is the call the
+ * reference-facing detector shell makes (bevformer_occ.py:247-250 returns CPU tensors). */
+int occb200_engine_forward_host(occb200_engine* e, const float* const* feats_host, int64_t* occ_cls_i64_host,
+                                float* flow_host, void* stream);
+
+/* Intermediate taps for parity tests (dev f32, valid after a forward; NULL if not produced):
+ *   which: 0 = layer output [Nq,C] of layer `layer`; 1 = TSA output (pre-norm, with residual); 2 = SCA output
+ *   (pre-norm, with residual); 3 = voxel features [X,Y,Z,out_dim] (converted to fp32 into `dst`). */
+int occb200_engine_enable_taps(occb200_engine* e, int enable);
+int occb200_engine_copy_tap(occb200_engine* e, int which, int layer, float* dst_dev, void* stream);
+
+/* Row a2 on its own: reference_points_cam dev f32 [num_cams, Nq, D, 2], bev_mask dev u8 [num_cams, Nq, D]. */
+int occb200_engine_project_pillars(occb200_engine* e, float* ref_cam, uint8_t* mask, void* stream);
+/* number of kernels one forward launches (for the benchmark's gpu_launches claim) */
+int occb200_engine_launches_per_frame(const occb200_engine* e);
+/* Per-kernel-category device timing with CUDA events on the launch stream (benchmark roofline).
+ * Categories: 0 pack/prepare, 1 dense GEMM, 2 TSA gather, 3 SCA gather, 4 LayerNorm, 5 bev->voxel, 6 conv3d,
+ * 7 occ/flow heads.  _profile(e,1) starts collecting, _profile_read synchronises and returns the summed
+ * milliseconds and launch counts since the last read (n >= 8). */
+int occb200_engine_profile(occb200_engine* e, int enable);
+int occb200_engine_profile_read(occb200_engine* e, float* ms_per_category, int* launches_per_category, int n);
+
+/* ---------------------------------------------------------------------------------------------
+ * [R3] dvr.render_forward (phase "test").  sigma dev f32 [N,T,Z,Y,X]; origin dev f32 [N,T,3];
+ * points dev f32 [N,M,3]; tindex dev f32 [N,M]; outputs dev f32 pred_dist [N,M], gt_dist [N,M],
+ * coord_index [N,M,3] (all written, including the -1 / 0 defaults).
+ */
+int occb200_render_forward(const float* sigma, const float* origin, const float* points, const float* tindex,
+                           int N, int T, int Z, int Y, int X, int64_t M, float* pred_dist, float* gt_dist,
+                           float* coord_index, void* stream);
+
+/* [R4] One frame of the Ray-mIoU / mAVE metric on a 200x200x16 grid (0.4 m voxels, range [-40,-40,-1]).
+ *   sem_* dev u8 [200,200,16]; flow_* dev f32 [200,200,16,2]; origins dev [T,3] (f32, or f64 if origin_is_f64);
+ *   rays dev f32 [M,3] (generate_lidar_rays); counters dev f64 [187] accumulated in place, layout
+ *   gt_cnt[17] pred_cnt[17] tp_cnt[3][17] ave[3][17] ave_count[3][17] (ray_metrics.py:149-158);
+ *   pcd_pred / pcd_gt dev f32 [T*M,4] optional (process_one_sample rows: class, dist, flow_x, flow_y). */
+int occb200_ray_metric_accumulate(const uint8_t* sem_pred, const float* flow_pred, const uint8_t* sem_gt,
+                                  const float* flow_gt, const void* origins, int origin_is_f64, int T,
+                                  const float* rays, int M, double* counters, float* pcd_pred, float* pcd_gt,
+                                  void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Building blocks exposed for the module-level API mirror and for kernel tests (dev pointers).
+ *   linear: C[M,N] = act(A[M,K] . W[N,K]^T + bias) (+ residual), fp32, act 0 none / 1 relu
+ *   layernorm: rows x 256, eps 1e-5 */
+int occb200_linear_f32(const float* A, const float* W, const float* bias, const float* residual, float* C, int M,
+                       int N, int K, int act, void* stream);
+int occb200_layernorm_f32(const float* x, const float* gamma, const float* beta, float* y, int rows, int C,
+                          void* stream);
+/* tcgen05 bf16 GEMM self-test entry: C f32 [M,N] = A bf16 [M,K] . W bf16 [N,K]^T (+bias); used by tests */
+int occb200_gemm_bf16_tc(const void* A_bf16, const void* W_bf16, const float* bias, float* C, int M, int N, int K,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCC_B200_H_ */

@@ -1,0 +1,654 @@
+// Host-side frame engine + C ABI (include/occ_b200.h).  One engine = one model replica on one GPU;
+// frames are independent (the reference always runs prev_bev=None, bevformer_occ.py:243-244), so the
+// multi-GPU story is one engine per rank and no data-path collective.
+//
+// Per-frame schedule (reference call stack: SURVEY section 3.1):
+//   pack_level x4        transformer_occ.py:207-227   (+cams_embeds, +level_embeds, NCHW -> tokens)
+//   per encoder layer    encoder.py:356-404           (self_attn, norm, cross_attn, norm, ffn, norm)
+//   bev_to_voxel, conv3d x2, occ_head                 transformer_occ.py:305-319, bevformer_occ_head.py:211-212
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/occ_b200.h"
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+namespace occ {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int alloc(size_t n) {
+        release();
+        if (n == 0) return 0;
+        OCC_CUDA(cudaMalloc(&p, n));
+        bytes = n;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <typename U> U* as() const { return reinterpret_cast<U*>(p); }
+};
+
+struct LayerW {
+    DevBuf tsa_v_w, tsa_v_b, tsa_q_w, tsa_q_b, tsa_o_w, tsa_o_b;
+    DevBuf sca_q_w, sca_q_b, sca_v_w, sca_v_b, sca_o_w, sca_o_b;
+    DevBuf ffn1_w, ffn1_b, ffn2_w, ffn2_b;
+    DevBuf ln_g[3], ln_b[3];
+    // bf16 copies for the tensor-core path
+    DevBuf tsa_v_wh, tsa_q_wh, tsa_o_wh, sca_q_wh, sca_v_wh, sca_o_wh, ffn1_wh, ffn2_wh;
+};
+
+}  // namespace
+}  // namespace occ
+
+using namespace occ;
+
+struct occb200_engine {
+    occb200_config cfg;
+    int Nq = 0, Nv = 0, C = 256;
+    LevelGeom lg;
+    ScaParams sp;
+    bool cameras_set = false, finalized = false, taps = false;
+    std::map<std::string, std::vector<float>> host_params;
+    std::vector<LayerW> layers;
+    DevBuf bev_queries, pos, cams_embeds, level_embeds;
+    DevBuf conv_w[2], conv_b[2], conv_wh[2];
+    DevBuf hw1, hb1, hw2, hb2, fw1, fb1, fw2, fb2, head_wh;
+    // workspace
+    DevBuf tokens, sca_value, q_f32, q_t, q_pos_t, q0_t, prev_t, tsa_value, tsa_value_prev, qproj, attn_out, x_f32,
+        ffn_h, vox0, vox1, vox2, hits;
+    DevBuf tap_layer, tap_tsa, tap_sca;
+    // host-buffer variant
+    DevBuf feats_dev[4], occ_i64_dev, flow_dev;
+    int launches = 0;
+    // optional per-kernel-category timing (CUDA events on the launch stream)
+    bool profiling = false;
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_events;
+    std::vector<cudaEvent_t> event_pool;
+    size_t event_used = 0;
+    size_t elt() const { return cfg.precision ? 2 : 4; }
+};
+
+namespace {
+
+int upload(DevBuf& b, const float* src, size_t n)
+{
+    if (b.alloc(n * sizeof(float))) return 2;
+    OCC_CUDA(cudaMemcpy(b.p, src, n * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int upload_bf16(DevBuf& b, const float* src, size_t n)
+{
+    std::vector<__nv_bfloat16> h(n);
+    for (size_t i = 0; i < n; ++i) h[i] = __float2bfloat16(src[i]);
+    if (b.alloc(n * 2)) return 2;
+    OCC_CUDA(cudaMemcpy(b.p, h.data(), n * 2, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+const std::vector<float>* find(const occb200_engine* e, const std::string& k, size_t numel)
+{
+    auto it = e->host_params.find(k);
+    if (it == e->host_params.end()) { set_last_error("missing parameter: " + k); return nullptr; }
+    if (it->second.size() != numel) {
+        set_last_error("parameter " + k + " has " + std::to_string(it->second.size()) + " elements, expected " +
+                       std::to_string(numel));
+        return nullptr;
+    }
+    return &it->second;
+}
+
+#define GETP(var, key, n)                            \
+    const std::vector<float>* var = find(e, key, n); \
+    if (!var) return 3;
+
+// ---- per-category timing.  Categories: 0 pack/prepare, 1 gemm, 2 tsa gather, 3 sca gather, 4 layernorm,
+//      5 bev_to_voxel, 6 conv3d, 7 occ head
+enum { CAT_PACK = 0, CAT_GEMM, CAT_TSA, CAT_SCA, CAT_LN, CAT_VOX, CAT_CONV, CAT_HEAD, CAT_COUNT };
+struct ProfScope {
+    occb200_engine* e; cudaStream_t st; int cat; cudaEvent_t a = nullptr, b = nullptr;
+    static cudaEvent_t get(occb200_engine* e) {
+        if (e->event_used == e->event_pool.size()) {
+            cudaEvent_t ev; cudaEventCreate(&ev); e->event_pool.push_back(ev);
+        }
+        return e->event_pool[e->event_used++];
+    }
+    ProfScope(occb200_engine* e_, cudaStream_t st_, int cat_) : e(e_), st(st_), cat(cat_) {
+        if (e->profiling) { a = get(e); b = get(e); cudaEventRecord(a, st); }
+    }
+    ~ProfScope() {
+        if (e->profiling) { cudaEventRecord(b, st); e->prof_events.push_back({cat, {a, b}}); }
+    }
+};
+
+// ---- GEMM dispatch: tensor-core path for bf16 operands when enabled, CUDA-core path otherwise
+template <typename TA, typename TC>
+int gemm(occb200_engine* e, const TA* A, const TA* A2, int K1, const float* W, const void* Wh, const float* bias,
+         const float* residual, TC* C, int M, int N, int K, int act, cudaStream_t st)
+{
+    e->launches++;
+    ProfScope ps(e, st, CAT_GEMM);
+    if constexpr (sizeof(TA) == 2) {
+        if (e->cfg.use_tensor_cores && Wh != nullptr && gemm_tc_supported(M, N, K, A2 != nullptr ? K1 : K)) {
+            return gemm_tc<TC>(reinterpret_cast<const bf16*>(A), reinterpret_cast<const bf16*>(A2), K1,
+                               reinterpret_cast<const bf16*>(Wh), bias, residual, C, M, N, K, act, st);
+        }
+    }
+    const int lda = A2 ? K1 : K;
+    return gemm_simt<TA, TC>(A, lda, A2, A2 ? K - K1 : 0, K1, W, bias, residual, N, C, N, M, N, K, act, st);
+}
+
+template <typename T>
+int forward_impl(occb200_engine* e, const float* const* feats, const float* prev_bev, float* bev_embed,
+                 float* occ_logits, float* flow, uint8_t* cls_u8, int64_t* cls_i64, cudaStream_t st)
+{
+    const occb200_config& c = e->cfg;
+    const int Nq = e->Nq, Nv = e->Nv, C = 256, ncam = c.num_cams;
+    e->launches = 0;
+    T* tokens = e->tokens.as<T>();
+    for (int l = 0; l < c.num_levels; ++l) {
+        ProfScope ps(e, st, CAT_PACK);
+        if (launch_pack_level<T>(feats[l], e->cams_embeds.as<float>(), e->level_embeds.as<float>() + l * C, ncam, C,
+                                 e->lg.h[l] * e->lg.w[l], Nv, e->lg.start[l], tokens, st)) return 2;
+        e->launches++;
+    }
+    float* q_f32 = e->q_f32.as<float>();
+    float* x_f32 = e->x_f32.as<float>();
+    T* q_t = e->q_t.as<T>();
+    T* q_pos_t = e->q_pos_t.as<T>();
+    const float* pos = e->pos.as<float>();
+    {
+        ProfScope ps(e, st, CAT_PACK);
+        if (launch_prepare_query<T>(e->bev_queries.as<float>(), pos, (int64_t)Nq * C, q_f32, q_t, q_pos_t, st)) return 2;
+    }
+    e->launches++;
+    const bool has_prev = prev_bev != nullptr;
+    if (has_prev) {
+        // encoder.py:204-209: value = stack([prev_bev, bev_query]) built ONCE before the layer loop, so
+        // queue 1 keeps seeing the layer-0 query in every layer.
+        if (launch_cast<T>(prev_bev, e->prev_t.as<T>(), (int64_t)Nq * C, st)) return 2;
+        if (launch_cast<T>(e->bev_queries.as<float>(), e->q0_t.as<T>(), (int64_t)Nq * C, st)) return 2;
+        e->launches += 2;
+    }
+    float* qproj = e->qproj.as<float>();
+    T* attn_out = e->attn_out.as<T>();
+    for (int l = 0; l < c.num_layers; ++l) {
+        LayerW& w = e->layers[l];
+        // ---- temporal self-attention (temporal_self_attention.py:177-272)
+        T* v_cur = e->tsa_value.as<T>();
+        T* v_prev = v_cur;
+        if (gemm<T, T>(e, has_prev ? e->q0_t.as<T>() : q_t, nullptr, 0, w.tsa_v_w.as<float>(), w.tsa_v_wh.p,
+                       w.tsa_v_b.as<float>(), nullptr, v_cur, Nq, C, C, ACT_NONE, st)) return 2;
+        if (has_prev) {
+            v_prev = e->tsa_value_prev.as<T>();
+            if (gemm<T, T>(e, e->prev_t.as<T>(), nullptr, 0, w.tsa_v_w.as<float>(), w.tsa_v_wh.p,
+                           w.tsa_v_b.as<float>(), nullptr, v_prev, Nq, C, C, ACT_NONE, st)) return 2;
+        }
+        const int nq_tsa = 2 * 8 * c.tsa_points * 3;   // offsets (x,y) + logits
+        if (gemm<T, float>(e, has_prev ? e->prev_t.as<T>() : q_t, q_pos_t, C, w.tsa_q_w.as<float>(), w.tsa_q_wh.p,
+                           w.tsa_q_b.as<float>(), nullptr, qproj, Nq, nq_tsa, 2 * C, ACT_NONE, st)) return 2;
+        {
+            ProfScope ps(e, st, CAT_TSA);
+            if (launch_tsa_fused<T>(v_prev, v_cur, qproj, c.bev_h, c.bev_w, attn_out, st)) return 2;
+        }
+        e->launches++;
+        if (gemm<T, float>(e, attn_out, nullptr, 0, w.tsa_o_w.as<float>(), w.tsa_o_wh.p, w.tsa_o_b.as<float>(), q_f32,
+                           x_f32, Nq, C, C, ACT_NONE, st)) return 2;
+        if (e->taps)
+            OCC_CUDA(cudaMemcpyAsync(e->tap_tsa.as<float>() + (size_t)l * Nq * C, x_f32, (size_t)Nq * C * 4,
+                                     cudaMemcpyDeviceToDevice, st));
+        {
+            ProfScope ps(e, st, CAT_LN);
+            if (launch_layernorm<T>(x_f32, w.ln_g[0].as<float>(), w.ln_b[0].as<float>(), nullptr, Nq, C, q_f32, q_t,
+                                    (T*)nullptr, st)) return 2;
+        }
+        e->launches++;
+        // ---- spatial cross-attention (spatial_cross_attention.py:128-175, :334-393)
+        const int nq_sca = 8 * c.num_levels * c.sca_points * 3;
+        if (gemm<T, float>(e, q_t, nullptr, 0, w.sca_q_w.as<float>(), w.sca_q_wh.p, w.sca_q_b.as<float>(), nullptr,
+                           qproj, Nq, nq_sca, C, ACT_NONE, st)) return 2;
+        if (gemm<T, T>(e, tokens, nullptr, 0, w.sca_v_w.as<float>(), w.sca_v_wh.p, w.sca_v_b.as<float>(), nullptr,
+                       e->sca_value.as<T>(), ncam * Nv, C, C, ACT_NONE, st)) return 2;
+        {
+            ProfScope ps(e, st, CAT_SCA);
+            if (launch_sca_fused<T>(e->sca_value.as<T>(), qproj, e->sp, e->lg, Nv, attn_out, e->hits.as<uint8_t>(), st))
+                return 2;
+        }
+        e->launches++;
+        if (gemm<T, float>(e, attn_out, nullptr, 0, w.sca_o_w.as<float>(), w.sca_o_wh.p, w.sca_o_b.as<float>(), q_f32,
+                           x_f32, Nq, C, C, ACT_NONE, st)) return 2;
+        if (e->taps)
+            OCC_CUDA(cudaMemcpyAsync(e->tap_sca.as<float>() + (size_t)l * Nq * C, x_f32, (size_t)Nq * C * 4,
+                                     cudaMemcpyDeviceToDevice, st));
+        {
+            ProfScope ps(e, st, CAT_LN);
+            if (launch_layernorm<T>(x_f32, w.ln_g[1].as<float>(), w.ln_b[1].as<float>(), nullptr, Nq, C, q_f32, q_t,
+                                    (T*)nullptr, st)) return 2;
+        }
+        e->launches++;
+        // ---- FFN (mmcv FFN: x + W2 relu(W1 x))
+        if (gemm<T, T>(e, q_t, nullptr, 0, w.ffn1_w.as<float>(), w.ffn1_wh.p, w.ffn1_b.as<float>(), nullptr,
+                       e->ffn_h.as<T>(), Nq, c.ffn_dim, C, ACT_RELU, st)) return 2;
+        if (gemm<T, float>(e, e->ffn_h.as<T>(), nullptr, 0, w.ffn2_w.as<float>(), w.ffn2_wh.p, w.ffn2_b.as<float>(),
+                           q_f32, x_f32, Nq, C, c.ffn_dim, ACT_NONE, st)) return 2;
+        {
+            ProfScope ps(e, st, CAT_LN);
+            if (launch_layernorm<T>(x_f32, w.ln_g[2].as<float>(), w.ln_b[2].as<float>(), pos, Nq, C, q_f32, q_t, q_pos_t,
+                                    st)) return 2;
+        }
+        e->launches++;
+        if (e->taps)
+            OCC_CUDA(cudaMemcpyAsync(e->tap_layer.as<float>() + (size_t)l * Nq * C, q_f32, (size_t)Nq * C * 4,
+                                     cudaMemcpyDeviceToDevice, st));
+    }
+    if (bev_embed)
+        OCC_CUDA(cudaMemcpyAsync(bev_embed, q_f32, (size_t)Nq * C * 4, cudaMemcpyDeviceToDevice, st));
+    if (!occ_logits && !flow && !cls_u8 && !cls_i64) return 0;
+    // ---- voxel decoder + heads
+    const int X = c.bev_w, Y = c.bev_h, Z = c.pillar_h, mid = C / Z;
+    {
+        ProfScope ps(e, st, CAT_VOX);
+        if (launch_bev_to_voxel<T>(q_f32, c.bev_h, c.bev_w, Z, mid, e->vox0.as<T>(), st)) return 2;
+    }
+    {
+        ProfScope ps(e, st, CAT_CONV);
+        if (launch_conv3d_simt<T>(e->vox0.as<T>(), e->conv_w[0].as<float>(), e->conv_b[0].as<float>(), X, Y, Z, mid,
+                                  e->vox1.as<T>(), st)) return 2;
+    }
+    {
+        ProfScope ps(e, st, CAT_CONV);
+        if (launch_conv3d_simt<T>(e->vox1.as<T>(), e->conv_w[1].as<float>(), e->conv_b[1].as<float>(), X, Y, Z,
+                                  c.out_dim, e->vox2.as<T>(), st)) return 2;
+    }
+    HeadWeights hw{e->hw1.as<float>(), e->hb1.as<float>(), e->hw2.as<float>(), e->hb2.as<float>(),
+                   e->fw1.as<float>(), e->fb1.as<float>(), e->fw2.as<float>(), e->fb2.as<float>(), c.num_classes};
+    {
+        ProfScope ps(e, st, CAT_HEAD);
+        if (launch_occ_head<T>(e->vox2.as<T>(), hw, (int64_t)X * Y * Z, occ_logits, flow, cls_u8, cls_i64, st)) return 2;
+    }
+    e->launches += 4;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* occb200_last_error(void) { return g_last_error.c_str(); }
+const char* occb200_version(void) { return "occ_b200 0.1 sm_100a"; }
+
+int occb200_ms_deform_attn_forward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                   const float* sampling_loc, const float* attn_weight, int B, int Nv, int M, int C,
+                                   int Nq, int L, int P, int im2col_step, float* out, void* stream)
+{
+    OCC_CHECK(value && spatial_shapes && level_start_index && sampling_loc && attn_weight && out, "null pointer");
+    OCC_CHECK(B >= 0 && Nv >= 0 && M > 0 && C > 0 && Nq >= 0 && L > 0 && P > 0, "bad sizes");
+    const int step = im2col_step < B ? im2col_step : B;
+    OCC_CHECK(B == 0 || (step > 0 && B % step == 0), "batch(" + std::to_string(B) + ") must divide im2col_step(" +
+                                                         std::to_string(im2col_step) + ")");
+    return launch_msda_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, B, Nv, M, C, Nq, L,
+                               P, out, (cudaStream_t)stream);
+}
+
+int occb200_engine_create(const occb200_config* cfg, occb200_engine** out)
+{
+    OCC_CHECK(cfg && out, "null pointer");
+    OCC_CHECK(cfg->embed_dims == 256 && cfg->num_heads == 8, "only embed_dims=256, num_heads=8 are supported");
+    OCC_CHECK(cfg->num_levels == 4 && cfg->sca_points == 8 && cfg->tsa_points == 4,
+              "only num_levels=4, SCA num_points=8, TSA num_points=4 are supported");
+    OCC_CHECK(cfg->num_cams >= 1 && cfg->num_cams <= 8, "num_cams must be in [1,8]");
+    OCC_CHECK(cfg->num_points_in_pillar >= 1 && cfg->num_points_in_pillar <= 8 && 8 % cfg->num_points_in_pillar == 0,
+              "num_points_in_pillar must be 1, 2, 4 or 8");
+    OCC_CHECK(cfg->pillar_h == 16 && cfg->out_dim == 32, "only pillar_h=16, out_dim=32 are supported");
+    OCC_CHECK(cfg->ffn_dim % 64 == 0 && cfg->num_classes <= 32 && cfg->num_layers >= 1, "bad ffn_dim/num_classes");
+    OCC_CHECK(cfg->precision == 0 || cfg->precision == 1, "precision must be 0 (fp32) or 1 (bf16)");
+    int dev_count = 0;
+    if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) {
+        set_last_error("no CUDA device: libocc_b200 has no CPU fallback");
+        return 4;
+    }
+    auto* e = new occb200_engine();
+    e->cfg = *cfg;
+    e->Nq = cfg->bev_h * cfg->bev_w;
+    e->lg.num_levels = 4;
+    int start = 0;
+    for (int l = 0; l < 4; ++l) {
+        e->lg.h[l] = cfg->level_h[l]; e->lg.w[l] = cfg->level_w[l]; e->lg.start[l] = start;
+        start += cfg->level_h[l] * cfg->level_w[l];
+    }
+    e->Nv = start;
+    e->layers.resize(cfg->num_layers);
+    *out = e;
+    return 0;
+}
+
+void occb200_engine_destroy(occb200_engine* e)
+{
+    if (!e) return;
+    // DevBuf members do not own a destructor on purpose (explicit release keeps teardown order obvious)
+    for (auto& w : e->layers) {
+        DevBuf* all[] = {&w.tsa_v_w, &w.tsa_v_b, &w.tsa_q_w, &w.tsa_q_b, &w.tsa_o_w, &w.tsa_o_b, &w.sca_q_w, &w.sca_q_b,
+                         &w.sca_v_w, &w.sca_v_b, &w.sca_o_w, &w.sca_o_b, &w.ffn1_w, &w.ffn1_b, &w.ffn2_w, &w.ffn2_b,
+                         &w.ln_g[0], &w.ln_g[1], &w.ln_g[2], &w.ln_b[0], &w.ln_b[1], &w.ln_b[2], &w.tsa_v_wh,
+                         &w.tsa_q_wh, &w.tsa_o_wh, &w.sca_q_wh, &w.sca_v_wh, &w.sca_o_wh, &w.ffn1_wh, &w.ffn2_wh};
+        for (DevBuf* b : all) b->release();
+    }
+    DevBuf* all[] = {&e->bev_queries, &e->pos, &e->cams_embeds, &e->level_embeds, &e->conv_w[0], &e->conv_w[1],
+                     &e->conv_b[0], &e->conv_b[1], &e->conv_wh[0], &e->conv_wh[1], &e->hw1, &e->hb1, &e->hw2, &e->hb2,
+                     &e->fw1, &e->fb1, &e->fw2, &e->fb2, &e->head_wh, &e->tokens, &e->sca_value, &e->q_f32, &e->q_t,
+                     &e->q_pos_t, &e->q0_t, &e->prev_t, &e->tsa_value, &e->tsa_value_prev, &e->qproj, &e->attn_out,
+                     &e->x_f32, &e->ffn_h, &e->vox0, &e->vox1, &e->vox2, &e->hits, &e->tap_layer, &e->tap_tsa,
+                     &e->tap_sca, &e->feats_dev[0], &e->feats_dev[1], &e->feats_dev[2], &e->feats_dev[3],
+                     &e->occ_i64_dev, &e->flow_dev};
+    for (DevBuf* b : all) b->release();
+    delete e;
+}
+
+int occb200_engine_load_param(occb200_engine* e, const char* key, const float* data, int64_t numel)
+{
+    OCC_CHECK(e && key && data && numel >= 0, "null pointer");
+    const std::string k(key);
+    static const char* known_prefix[] = {"bev_embedding.", "positional_encoding.", "transformer.level_embeds",
+                                         "transformer.cams_embeds", "transformer.encoder.layers.",
+                                         "transformer.decoder.", "transformer.predicter.", "transformer.flow_predicter."};
+    bool ok = false;
+    for (const char* p : known_prefix) ok = ok || k.rfind(p, 0) == 0;
+    if (!ok) { set_last_error("unknown parameter key: " + k); return 3; }
+    e->host_params[k].assign(data, data + numel);
+    e->finalized = false;
+    return 0;
+}
+
+int occb200_engine_finalize(occb200_engine* e)
+{
+    OCC_CHECK(e, "null engine");
+    const occb200_config& c = e->cfg;
+    const int C = 256, Nq = e->Nq, F = c.ffn_dim, od = c.out_dim, mid = C / c.pillar_h;
+    const bool tc = c.precision == 1 && c.use_tensor_cores;
+    {
+        GETP(bq, "bev_embedding.weight", (size_t)Nq * C);
+        if (upload(e->bev_queries, bq->data(), bq->size())) return 2;
+        GETP(re, "positional_encoding.row_embed.weight", (size_t)c.bev_h * (C / 2));
+        GETP(ce, "positional_encoding.col_embed.weight", (size_t)c.bev_w * (C / 2));
+        DevBuf dre, dce;
+        if (upload(dre, re->data(), re->size()) || upload(dce, ce->data(), ce->size())) return 2;
+        if (e->pos.alloc((size_t)Nq * C * 4)) return 2;
+        if (launch_bev_pos(dre.as<float>(), dce.as<float>(), c.bev_h, c.bev_w, C / 2, e->pos.as<float>(), 0)) return 2;
+        OCC_CUDA(cudaDeviceSynchronize());
+        dre.release(); dce.release();
+        GETP(le, "transformer.level_embeds", (size_t)c.num_levels * C);
+        GETP(cm, "transformer.cams_embeds", (size_t)c.num_cams * C);
+        if (upload(e->level_embeds, le->data(), le->size()) || upload(e->cams_embeds, cm->data(), cm->size())) return 2;
+    }
+    for (int l = 0; l < c.num_layers; ++l) {
+        LayerW& w = e->layers[l];
+        const std::string pre = "transformer.encoder.layers." + std::to_string(l);
+        const std::string a0 = pre + ".attentions.0", a1 = pre + ".attentions.1", d = a1 + ".deformable_attention";
+        auto up = [&](DevBuf& wbuf, DevBuf& bbuf, DevBuf* wh, const std::string& name, size_t n, size_t k) -> int {
+            const std::vector<float>* W = find(e, name + ".weight", n * k);
+            const std::vector<float>* B = find(e, name + ".bias", n);
+            if (!W || !B) return 3;
+            if (upload(wbuf, W->data(), W->size()) || upload(bbuf, B->data(), B->size())) return 2;
+            if (tc && wh && upload_bf16(*wh, W->data(), W->size())) return 2;
+            return 0;
+        };
+        auto up_cat = [&](DevBuf& wbuf, DevBuf& bbuf, DevBuf* wh, const std::string& n1, const std::string& n2,
+                          size_t r1, size_t r2, size_t k) -> int {
+            const std::vector<float>* W1 = find(e, n1 + ".weight", r1 * k);
+            const std::vector<float>* B1 = find(e, n1 + ".bias", r1);
+            const std::vector<float>* W2 = find(e, n2 + ".weight", r2 * k);
+            const std::vector<float>* B2 = find(e, n2 + ".bias", r2);
+            if (!W1 || !B1 || !W2 || !B2) return 3;
+            std::vector<float> W(*W1), B(*B1);
+            W.insert(W.end(), W2->begin(), W2->end());
+            B.insert(B.end(), B2->begin(), B2->end());
+            if (upload(wbuf, W.data(), W.size()) || upload(bbuf, B.data(), B.size())) return 2;
+            if (tc && wh && upload_bf16(*wh, W.data(), W.size())) return 2;
+            return 0;
+        };
+        int rc;
+        const size_t tq_off = 2 * 8 * c.tsa_points * 2, tq_w = 2 * 8 * c.tsa_points;
+        const size_t sq_off = 8 * c.num_levels * c.sca_points * 2, sq_w = 8 * c.num_levels * c.sca_points;
+        if ((rc = up(w.tsa_v_w, w.tsa_v_b, &w.tsa_v_wh, a0 + ".value_proj", C, C))) return rc;
+        if ((rc = up_cat(w.tsa_q_w, w.tsa_q_b, &w.tsa_q_wh, a0 + ".sampling_offsets", a0 + ".attention_weights", tq_off,
+                         tq_w, 2 * C))) return rc;
+        if ((rc = up(w.tsa_o_w, w.tsa_o_b, &w.tsa_o_wh, a0 + ".output_proj", C, C))) return rc;
+        if ((rc = up_cat(w.sca_q_w, w.sca_q_b, &w.sca_q_wh, d + ".sampling_offsets", d + ".attention_weights", sq_off,
+                         sq_w, C))) return rc;
+        if ((rc = up(w.sca_v_w, w.sca_v_b, &w.sca_v_wh, d + ".value_proj", C, C))) return rc;
+        if ((rc = up(w.sca_o_w, w.sca_o_b, &w.sca_o_wh, a1 + ".output_proj", C, C))) return rc;
+        if ((rc = up(w.ffn1_w, w.ffn1_b, &w.ffn1_wh, pre + ".ffns.0.layers.0.0", F, C))) return rc;
+        if ((rc = up(w.ffn2_w, w.ffn2_b, &w.ffn2_wh, pre + ".ffns.0.layers.1", C, F))) return rc;
+        for (int n = 0; n < 3; ++n) {
+            GETP(g, pre + ".norms." + std::to_string(n) + ".weight", (size_t)C);
+            GETP(b, pre + ".norms." + std::to_string(n) + ".bias", (size_t)C);
+            if (upload(w.ln_g[n], g->data(), C) || upload(w.ln_b[n], b->data(), C)) return 2;
+        }
+    }
+    // decoder: fold BatchNorm3d (eval) into the conv weights; torch layout [Cout][Cin][kz][ky][kx] -> [tap][Cin][Cout]
+    for (int i = 0; i < 2; ++i) {
+        const int cin = i == 0 ? mid : od;
+        const std::string pre = "transformer.decoder." + std::to_string(i);
+        GETP(W, pre + ".conv.weight", (size_t)od * cin * 27);
+        GETP(g, pre + ".bn.weight", (size_t)od);
+        GETP(b, pre + ".bn.bias", (size_t)od);
+        GETP(m, pre + ".bn.running_mean", (size_t)od);
+        GETP(v, pre + ".bn.running_var", (size_t)od);
+        std::vector<float> wf((size_t)27 * cin * od), bf(od);
+        for (int co = 0; co < od; ++co) {
+            const float s = (*g)[co] / sqrtf((*v)[co] + 1e-5f);
+            bf[co] = (*b)[co] - (*m)[co] * s;
+            for (int ci = 0; ci < cin; ++ci)
+                for (int t = 0; t < 27; ++t)
+                    wf[((size_t)t * cin + ci) * od + co] = (*W)[((size_t)co * cin + ci) * 27 + t] * s;
+        }
+        if (upload(e->conv_w[i], wf.data(), wf.size()) || upload(e->conv_b[i], bf.data(), bf.size())) return 2;
+    }
+    {
+        GETP(w1, "transformer.predicter.0.weight", (size_t)2 * od * od);
+        GETP(b1, "transformer.predicter.0.bias", (size_t)2 * od);
+        GETP(w2, "transformer.predicter.2.weight", (size_t)c.num_classes * 2 * od);
+        GETP(b2, "transformer.predicter.2.bias", (size_t)c.num_classes);
+        GETP(f1, "transformer.flow_predicter.0.weight", (size_t)2 * od * od);
+        GETP(g1, "transformer.flow_predicter.0.bias", (size_t)2 * od);
+        GETP(f2, "transformer.flow_predicter.2.weight", (size_t)2 * 2 * od);
+        GETP(g2, "transformer.flow_predicter.2.bias", (size_t)2);
+        if (upload(e->hw1, w1->data(), w1->size()) || upload(e->hb1, b1->data(), b1->size()) ||
+            upload(e->hw2, w2->data(), w2->size()) || upload(e->hb2, b2->data(), b2->size()) ||
+            upload(e->fw1, f1->data(), f1->size()) || upload(e->fb1, g1->data(), g1->size()) ||
+            upload(e->fw2, f2->data(), f2->size()) || upload(e->fb2, g2->data(), g2->size())) return 2;
+    }
+    // workspace
+    const size_t es = e->elt();
+    const size_t nvox = (size_t)c.bev_w * c.bev_h * c.pillar_h;
+    const size_t ntok = (size_t)c.num_cams * e->Nv;
+    int maxq = 8 * c.num_levels * c.sca_points * 3;
+    if (e->tokens.alloc(ntok * C * es) || e->sca_value.alloc(ntok * C * es) || e->q_f32.alloc((size_t)Nq * C * 4) ||
+        e->q_t.alloc((size_t)Nq * C * es) || e->q_pos_t.alloc((size_t)Nq * C * es) || e->q0_t.alloc((size_t)Nq * C * es) ||
+        e->prev_t.alloc((size_t)Nq * C * es) || e->tsa_value.alloc((size_t)Nq * C * es) ||
+        e->tsa_value_prev.alloc((size_t)Nq * C * es) || e->qproj.alloc((size_t)Nq * maxq * 4) ||
+        e->attn_out.alloc((size_t)Nq * C * es) || e->x_f32.alloc((size_t)Nq * C * 4) ||
+        e->ffn_h.alloc((size_t)Nq * F * es) || e->vox0.alloc(nvox * mid * es) || e->vox1.alloc(nvox * od * es) ||
+        e->vox2.alloc(nvox * od * es) || e->hits.alloc(Nq)) return 2;
+    e->host_params.clear();
+    e->finalized = true;
+    return 0;
+}
+
+int occb200_engine_set_cameras(occb200_engine* e, const float* cam_mat, const float* zs, int img_h, int img_w)
+{
+    OCC_CHECK(e && cam_mat && zs, "null pointer");
+    const occb200_config& c = e->cfg;
+    memset(&e->sp, 0, sizeof(e->sp));
+    for (int i = 0; i < c.num_cams; ++i)
+        for (int k = 0; k < 16; ++k) e->sp.cam_mat[i][k] = cam_mat[i * 16 + k];
+    for (int i = 0; i < c.num_points_in_pillar; ++i) e->sp.zs[i] = zs[i];
+    for (int i = 0; i < 3; ++i) {
+        e->sp.pc_scale[i] = (float)((double)c.pc_range[3 + i] - (double)c.pc_range[i]);
+        e->sp.pc_min[i] = c.pc_range[i];
+    }
+    e->sp.img_w = (float)img_w; e->sp.img_h = (float)img_h;
+    e->sp.num_cams = c.num_cams; e->sp.D = c.num_points_in_pillar; e->sp.bev_h = c.bev_h; e->sp.bev_w = c.bev_w;
+    e->cameras_set = true;
+    return 0;
+}
+
+int occb200_engine_forward(occb200_engine* e, const float* const* feats, const float* prev_bev, float* bev_embed,
+                           float* occ_logits, float* flow, uint8_t* occ_cls_u8, int64_t* occ_cls_i64, void* stream)
+{
+    OCC_CHECK(e && feats, "null pointer");
+    OCC_CHECK(e->finalized, "engine_finalize() has not been called");
+    OCC_CHECK(e->cameras_set, "engine_set_cameras() has not been called");
+    for (int l = 0; l < e->cfg.num_levels; ++l) OCC_CHECK(feats[l] != nullptr, "null feature level");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (e->cfg.precision == 0)
+        return forward_impl<float>(e, feats, prev_bev, bev_embed, occ_logits, flow, occ_cls_u8, occ_cls_i64, st);
+    return forward_impl<bf16>(e, feats, prev_bev, bev_embed, occ_logits, flow, occ_cls_u8, occ_cls_i64, st);
+}
+
+int occb200_engine_forward_host(occb200_engine* e, const float* const* feats_host, int64_t* occ_cls_i64_host,
+                                float* flow_host, void* stream)
+{
+    OCC_CHECK(e && feats_host && occ_cls_i64_host && flow_host, "null pointer");
+    OCC_CHECK(e->finalized && e->cameras_set, "engine not finalized / cameras not set");
+    const occb200_config& c = e->cfg;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nvox = (size_t)c.bev_w * c.bev_h * c.pillar_h;
+    const float* dev_feats[4];
+    for (int l = 0; l < 4; ++l) {
+        const size_t n = (size_t)c.num_cams * 256 * e->lg.h[l] * e->lg.w[l] * 4;
+        if (e->feats_dev[l].bytes != n && e->feats_dev[l].alloc(n)) return 2;
+        OCC_CUDA(cudaMemcpyAsync(e->feats_dev[l].p, feats_host[l], n, cudaMemcpyHostToDevice, st));
+        dev_feats[l] = e->feats_dev[l].as<float>();
+    }
+    if (e->occ_i64_dev.bytes != nvox * 8 && e->occ_i64_dev.alloc(nvox * 8)) return 2;
+    if (e->flow_dev.bytes != nvox * 8 && e->flow_dev.alloc(nvox * 8)) return 2;
+    int rc = occb200_engine_forward(e, dev_feats, nullptr, nullptr, nullptr, e->flow_dev.as<float>(), nullptr,
+                                    e->occ_i64_dev.as<int64_t>(), stream);
+    if (rc) return rc;
+    OCC_CUDA(cudaMemcpyAsync(occ_cls_i64_host, e->occ_i64_dev.p, nvox * 8, cudaMemcpyDeviceToHost, st));
+    OCC_CUDA(cudaMemcpyAsync(flow_host, e->flow_dev.p, nvox * 8, cudaMemcpyDeviceToHost, st));
+    OCC_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int occb200_engine_enable_taps(occb200_engine* e, int enable)
+{
+    OCC_CHECK(e && e->finalized, "engine not finalized");
+    e->taps = enable != 0;
+    if (e->taps) {
+        const size_t n = (size_t)e->cfg.num_layers * e->Nq * 256 * 4;
+        if (e->tap_layer.alloc(n) || e->tap_tsa.alloc(n) || e->tap_sca.alloc(n)) return 2;
+    }
+    return 0;
+}
+
+int occb200_engine_copy_tap(occb200_engine* e, int which, int layer, float* dst, void* stream)
+{
+    OCC_CHECK(e && dst, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)e->Nq * 256;
+    if (which >= 0 && which <= 2) {
+        OCC_CHECK(e->taps && layer >= 0 && layer < e->cfg.num_layers, "taps not enabled or bad layer");
+        const DevBuf& b = which == 0 ? e->tap_layer : (which == 1 ? e->tap_tsa : e->tap_sca);
+        OCC_CUDA(cudaMemcpyAsync(dst, b.as<float>() + layer * n, n * 4, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    if (which == 3) {
+        const size_t nv = (size_t)e->cfg.bev_w * e->cfg.bev_h * e->cfg.pillar_h * e->cfg.out_dim;
+        if (e->cfg.precision == 0) {
+            OCC_CUDA(cudaMemcpyAsync(dst, e->vox2.p, nv * 4, cudaMemcpyDeviceToDevice, st));
+            return 0;
+        }
+        return launch_bf16_to_f32(e->vox2.as<bf16>(), dst, (int64_t)nv, st);
+    }
+    set_last_error("unknown tap");
+    return 1;
+}
+
+int occb200_engine_project_pillars(occb200_engine* e, float* ref_cam, uint8_t* mask, void* stream)
+{
+    OCC_CHECK(e && ref_cam && mask && e->cameras_set, "null pointer / cameras not set");
+    return launch_project_pillars(e->sp, ref_cam, mask, (cudaStream_t)stream);
+}
+
+int occb200_engine_launches_per_frame(const occb200_engine* e) { return e ? e->launches : 0; }
+
+int occb200_engine_profile(occb200_engine* e, int enable)
+{
+    OCC_CHECK(e, "null engine");
+    e->profiling = enable != 0;
+    e->prof_events.clear();
+    e->event_used = 0;
+    return 0;
+}
+
+int occb200_engine_profile_read(occb200_engine* e, float* ms_per_category, int* launches_per_category, int n)
+{
+    OCC_CHECK(e && ms_per_category && launches_per_category && n >= CAT_COUNT, "bad arguments");
+    OCC_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < n; ++i) { ms_per_category[i] = 0.f; launches_per_category[i] = 0; }
+    for (auto& pe : e->prof_events) {
+        float ms = 0.f;
+        OCC_CUDA(cudaEventElapsedTime(&ms, pe.second.first, pe.second.second));
+        ms_per_category[pe.first] += ms;
+        launches_per_category[pe.first] += 1;
+    }
+    e->prof_events.clear();
+    e->event_used = 0;
+    return 0;
+}
+
+int occb200_render_forward(const float* sigma, const float* origin, const float* points, const float* tindex, int N,
+                           int T, int Z, int Y, int X, int64_t M, float* pred_dist, float* gt_dist, float* coord_index,
+                           void* stream)
+{
+    OCC_CHECK(sigma && origin && points && tindex && pred_dist && gt_dist && coord_index, "null pointer");
+    return launch_render_forward(sigma, origin, points, tindex, N, T, Z, Y, X, M, pred_dist, gt_dist, coord_index,
+                                 (cudaStream_t)stream);
+}
+
+int occb200_ray_metric_accumulate(const uint8_t* sem_pred, const float* flow_pred, const uint8_t* sem_gt,
+                                  const float* flow_gt, const void* origins, int origin_is_f64, int T, const float* rays,
+                                  int M, double* counters, float* pcd_pred, float* pcd_gt, void* stream)
+{
+    OCC_CHECK(sem_pred && flow_pred && sem_gt && flow_gt && origins && rays && counters, "null pointer");
+    return launch_ray_metric(sem_pred, flow_pred, sem_gt, flow_gt, origins, origin_is_f64, T, rays, M, counters,
+                             pcd_pred, pcd_gt, (cudaStream_t)stream);
+}
+
+int occb200_linear_f32(const float* A, const float* W, const float* bias, const float* residual, float* C, int M, int N,
+                       int K, int act, void* stream)
+{
+    OCC_CHECK(A && W && C, "null pointer");
+    return gemm_simt<float, float>(A, K, nullptr, 0, K, W, bias, residual, N, C, N, M, N, K, act, (cudaStream_t)stream);
+}
+
+int occb200_layernorm_f32(const float* x, const float* gamma, const float* beta, float* y, int rows, int C, void* stream)
+{
+    OCC_CHECK(x && gamma && beta && y, "null pointer");
+    return launch_layernorm<float>(x, gamma, beta, nullptr, rows, C, y, (float*)nullptr, (float*)nullptr,
+                                   (cudaStream_t)stream);
+}
+
+int occb200_gemm_bf16_tc(const void* A, const void* W, const float* bias, float* C, int M, int N, int K, void* stream)
+{
+    OCC_CHECK(A && W && C, "null pointer");
+    OCC_CHECK(gemm_tc_supported(M, N, K, K), "shape not supported by the tcgen05 GEMM");
+    return gemm_tc<float>(reinterpret_cast<const bf16*>(A), nullptr, 0, reinterpret_cast<const bf16*>(W), bias, nullptr,
+                          C, M, N, K, ACT_NONE, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,16 @@
+// tcgen05 / TMEM / TMA bf16 GEMM (gemm_tc.cu):  C[M,N] = act(A[M,K] . W[N,K]^T + bias) (+ residual)
+#pragma once
+#include "common.cuh"
+
+namespace occ {
+
+// shapes the tensor-core kernel handles: K % 64 == 0 (and the split point K1 % 64 == 0), N % 16 == 0, N <= 256 per pass
+bool gemm_tc_supported(int M, int N, int K, int K1);
+
+template <typename TC>
+int gemm_tc(const bf16* A, const bf16* A2, int K1, const bf16* W, const float* bias, const float* residual, TC* C,
+            int M, int N, int K, int act, cudaStream_t stream);
+
+int launch_bf16_to_f32(const bf16* src, float* dst, int64_t n, cudaStream_t stream);
+
+}  // namespace occ

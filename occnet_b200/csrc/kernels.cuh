@@ -1,0 +1,76 @@
+// Launcher declarations shared by the engine (engine.cu) and the C-ABI (capi.cu).
+#pragma once
+#include "common.cuh"
+
+namespace occ {
+
+// Per-frame camera geometry for the fused spatial cross-attention kernel.
+struct ScaParams {
+    float cam_mat[8][16];   // lidar2img[c] @ ego2lidar, fp32 row-major (encoder.py:126)
+    float zs[8];            // normalised pillar heights linspace(.5, Z-.5, D)/Z (encoder.py:66-67)
+    float pc_scale[3];      // pc_range[3+i] - pc_range[i]
+    float pc_min[3];        // pc_range[i]
+    float img_w, img_h;     // padded image size of batch item 0 (encoder.py:133-134)
+    int num_cams, D, bev_h, bev_w;
+};
+
+// ---- msda.cu
+int launch_msda_forward(const float* value, const int64_t* shapes, const int64_t* lstart, const float* loc,
+                        const float* wts, int B, int Nv, int M, int C, int Nq, int L, int P, float* out,
+                        cudaStream_t stream);
+template <typename T>
+int launch_tsa_fused(const T* value_prev, const T* value_cur, const float* qproj, int bev_h, int bev_w, T* out,
+                     cudaStream_t stream);
+template <typename T>
+int launch_sca_fused(const T* value, const float* qproj, const ScaParams& sp, const LevelGeom& lg, int Nv, T* out,
+                     uint8_t* hits, cudaStream_t stream);
+int launch_project_pillars(const ScaParams& sp, float* ref_cam, uint8_t* mask, cudaStream_t stream);
+
+// ---- elementwise.cu
+// feats level l: [num_cams, C, h, w] f32 (NCHW) -> tokens [num_cams, Nv, C] T, + cams_embeds + level_embeds
+template <typename T>
+int launch_pack_level(const float* feat, const float* cams_embeds, const float* level_embed, int num_cams, int C,
+                      int hw, int Nv, int start, T* tokens, cudaStream_t stream);
+// y = LayerNorm(x) (eps 1e-5); writes fp32 copy (residual stream), T copy (GEMM operand) and T copy of y + pos
+template <typename T>
+int launch_layernorm(const float* x, const float* gamma, const float* beta, const float* pos, int rows, int C,
+                     float* y_f32, T* y_t, T* y_pos_t, cudaStream_t stream);
+// bev_queries [Nq,C] f32 -> f32 copy, T copy, T copy + pos (layer-0 input)
+template <typename T>
+int launch_prepare_query(const float* bev_queries, const float* pos, int64_t n, float* q_f32, T* q_t, T* q_pos_t,
+                         cudaStream_t stream);
+// pos[q, :] = cat(col_embed[q % W], row_embed[q / W])     (mmdet LearnedPositionalEncoding)
+int launch_bev_pos(const float* row_embed, const float* col_embed, int bev_h, int bev_w, int half, float* pos,
+                   cudaStream_t stream);
+template <typename T>
+int launch_cast(const float* src, T* dst, int64_t n, cudaStream_t stream);
+
+// ---- decoder_simt.cu
+// bev [Nq = H*W, C = mid*Z] f32 -> vox [X=W][Y=H][Z][mid] T with vox[x][y][z][cm] = bev[y*W+x][cm*Z+z]
+template <typename T>
+int launch_bev_to_voxel(const float* bev, int bev_h, int bev_w, int Z, int mid, T* vox, cudaStream_t stream);
+// 3x3x3 conv (pad 1) + folded BatchNorm + ReLU on channels-last [X][Y][Z][Cin] -> [X][Y][Z][Cout=32]
+// wfold: [27][Cin][32] f32 (tap = (dz*3+dy)*3+dx), bfold: [32]
+template <typename T>
+int launch_conv3d_simt(const T* in, const float* wfold, const float* bfold, int X, int Y, int Z, int Cin, T* out,
+                       cudaStream_t stream);
+// per-voxel heads: occ = W2 softplus(W1 f + b1) + b2 (17), flow = W2' relu(W1' f + b1') + b2' (2), cls = argmax
+struct HeadWeights {
+    const float *w1, *b1, *w2, *b2;       // predicter:      [64,32],[64],[ncls,64],[ncls]
+    const float *fw1, *fb1, *fw2, *fb2;   // flow_predicter: [64,32],[64],[2,64],[2]
+    int ncls;
+};
+template <typename T>
+int launch_occ_head(const T* vox, HeadWeights hw, int64_t nvox, float* occ_logits, float* flow, uint8_t* cls_u8,
+                    int64_t* cls_i64, cudaStream_t stream);
+
+// ---- raycast.cu
+// rows a14/a15: DDA first-hit for T origins x M rays through pred and gt volumes + the 187 counters
+int launch_render_forward(const float* sigma, const float* origin, const float* points, const float* tindex,
+                          int N, int T, int Z, int Y, int X, int64_t M, float* pred_dist, float* gt_dist,
+                          float* coord_index, cudaStream_t stream);
+int launch_ray_metric(const uint8_t* sem_pred, const float* flow_pred, const uint8_t* sem_gt, const float* flow_gt,
+                      const void* origins, int origin_is_f64, int T, const float* rays, int M, double* counters,
+                      float* pcd_pred, float* pcd_gt, cudaStream_t stream);
+
+}  // namespace occ

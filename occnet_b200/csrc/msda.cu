@@ -1,0 +1,357 @@
+// Multi-scale deformable attention for sm_100a: the operator-boundary kernel (mmcv `_ext` ABI
+// semantics) and the two fused BEVFormer variants.
+//
+//   msda_forward_kernel  <- mmcv._ext.ms_deform_attn_forward, called from
+//        bevformer/modules/multi_scale_deformable_attn_function.py:118-124
+//   tsa_fused_kernel     <- TemporalSelfAttention.forward, temporal_self_attention.py:206-262
+//        (softmax over points, sampling locations, gather, mean over the BEV queue)
+//   sca_fused_kernel     <- BEVFormerEncoder.point_sampling (encoder.py:92-151) +
+//        SpatialCrossAttention.forward (spatial_cross_attention.py:128-172) +
+//        MSDeformableAttention3D.forward (:338-393): camera projection of the pillar points,
+//        visibility, softmax, Z-anchor interleave, gather, cross-camera sum and /count --
+//        without the reference's nonzero() host sync, rebatch copies and scatter loops.
+//
+// Mapping (both fused kernels): one warp per BEV query; lane = (head = lane/4, slice = lane%4);
+// a lane accumulates 8 of the head's 32 channels, so one warp-wide 128-bit load instruction
+// fetches 8 independent 64-byte (bf16) corner rows.  Per-sample scalars (location, weight) live
+// in one owner lane per (head, level) and are broadcast inside the 4-lane group with shuffles.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace occ {
+
+namespace {
+
+// bilinear gather of 8 channels with zero padding; `base` points at (level start, head, slice),
+// consecutive pixels are `pix_stride` elements apart.  Same validity rules as the mmcv kernel.
+template <typename T>
+__device__ __forceinline__ void bilinear_acc8(const T* __restrict__ base, int H, int W, int pix_stride,
+                                              float h_im, float w_im, float wt, float (&acc)[8])
+{
+    if (!(h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W)) return;
+    const int h_lo = (int)floorf(h_im), w_lo = (int)floorf(w_im);
+    const float lh = h_im - (float)h_lo, lw = w_im - (float)w_lo;
+    const float hh = 1.f - lh, hw = 1.f - lw;
+    const bool top = h_lo >= 0, bot = h_lo + 1 <= H - 1, lef = w_lo >= 0, rig = w_lo + 1 <= W - 1;
+    const T* p = base + ((int64_t)h_lo * W + w_lo) * pix_stride;
+    float v1[8], v2[8], v3[8], v4[8];
+    const bool b1 = top && lef, b2 = top && rig, b3 = bot && lef, b4 = bot && rig;
+    if (b1) load8(p, v1);
+    if (b2) load8(p + pix_stride, v2);
+    if (b3) load8(p + (int64_t)W * pix_stride, v3);
+    if (b4) load8(p + (int64_t)(W + 1) * pix_stride, v4);
+    const float w1 = b1 ? wt * (hh * hw) : 0.f, w2 = b2 ? wt * (hh * lw) : 0.f;
+    const float w3 = b3 ? wt * (lh * hw) : 0.f, w4 = b4 ? wt * (lh * lw) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float a = acc[i];
+        if (b1) a = fmaf(w1, v1[i], a);
+        if (b2) a = fmaf(w2, v2[i], a);
+        if (b3) a = fmaf(w3, v3[i], a);
+        if (b4) a = fmaf(w4, v4[i], a);
+        acc[i] = a;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Operator boundary: value [B,Nv,M,C] f32, loc [B,Nq,M,L,P,2] (x,y), w [B,Nq,M,L,P] -> [B,Nq,M*C]
+// One thread per (b, q, head, 8-channel slice) when C % 8 == 0, otherwise per channel.
+template <int VEC>
+__global__ void msda_forward_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
+                                    const int64_t* __restrict__ lstart, const float* __restrict__ loc,
+                                    const float* __restrict__ wts, int B, int Nv, int M, int C, int Nq,
+                                    int L, int P, float* __restrict__ out)
+{
+    const int slices = C / VEC;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)B * Nq * M * slices;
+    if (idx >= total) return;
+    const int s = (int)(idx % slices);
+    const int m = (int)((idx / slices) % M);
+    const int64_t bq = idx / ((int64_t)slices * M);           // b * Nq + q
+    const int b = (int)(bq / Nq);
+    const float* lp = loc + (bq * M + m) * (int64_t)L * P * 2;
+    const float* wp = wts + (bq * M + m) * (int64_t)L * P;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int l = 0; l < L; ++l) {
+        const int H = (int)shapes[2 * l], W = (int)shapes[2 * l + 1];
+        const float* base = value + (((int64_t)b * Nv + lstart[l]) * M + m) * C + s * VEC;
+        for (int p = 0; p < P; ++p) {
+            const float w_im = lp[(l * P + p) * 2] * (float)W - 0.5f;
+            const float h_im = lp[(l * P + p) * 2 + 1] * (float)H - 0.5f;
+            const float wt = wp[l * P + p];
+            if constexpr (VEC == 8) {
+                bilinear_acc8<float>(base, H, W, M * C, h_im, w_im, wt, acc);
+            } else {
+                if (!(h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W)) continue;
+                const int h_lo = (int)floorf(h_im), w_lo = (int)floorf(w_im);
+                const float lh = h_im - h_lo, lw = w_im - w_lo, hh = 1.f - lh, hw = 1.f - lw;
+                const int64_t st = (int64_t)M * C;
+                const float* q = base + ((int64_t)h_lo * W + w_lo) * st;
+                float v = 0.f;
+                if (h_lo >= 0 && w_lo >= 0) v += hh * hw * q[0];
+                if (h_lo >= 0 && w_lo + 1 <= W - 1) v += hh * lw * q[st];
+                if (h_lo + 1 <= H - 1 && w_lo >= 0) v += lh * hw * q[(int64_t)W * st];
+                if (h_lo + 1 <= H - 1 && w_lo + 1 <= W - 1) v += lh * lw * q[(int64_t)(W + 1) * st];
+                acc[0] += wt * v;
+            }
+        }
+    }
+    float* o = out + (bq * M + m) * C + s * VEC;
+    if constexpr (VEC == 8) store8(o, acc);
+    else o[0] = acc[0];
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused temporal self-attention gather.  qproj [Nq,192] f32 = Linear outputs
+//   [0,128):  sampling_offsets viewed (head, queue, level=1, point, xy)   (:206-208)
+//   [128,192): attention logits viewed (head, queue, point), softmax over the 4 points (:209-211)
+// value_prev / value_cur: [Nq, 8, 32] T (projected values of queue 0 / queue 1).
+// out[q] = 0.5 * (MSDA_queue0 + MSDA_queue1)                                (:257-262)
+template <typename T>
+__global__ void __launch_bounds__(256)
+tsa_fused_kernel(const T* __restrict__ value_prev, const T* __restrict__ value_cur,
+                 const float* __restrict__ qproj, int bev_h, int bev_w, T* __restrict__ out)
+{
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int Nq = bev_h * bev_w;
+    if (q >= Nq) return;
+    const int lane = threadIdx.x & 31, head = lane >> 2, s = lane & 3;
+    const int qu_own = s >> 1, p0 = (s & 1) * 2;              // owner of samples (queue, p0), (queue, p0+1)
+    const float* qp = qproj + (int64_t)q * 192;
+    // offsets of my two samples: index head*16 + queue*8 + p*2 + xy -> 4 consecutive floats
+    const float4 off = __ldg(reinterpret_cast<const float4*>(qp + head * 16 + qu_own * 8 + p0 * 2));
+    const float2 lg = __ldg(reinterpret_cast<const float2*>(qp + 128 + head * 8 + qu_own * 4 + p0));
+    // softmax over the 4 points of (head, queue): my 2 logits + partner lane (s ^ 1)
+    float mx = fmaxf(lg.x, lg.y);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    const float e0 = expf(lg.x - mx), e1 = expf(lg.y - mx);
+    float sum = e0 + e1;
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    const float wt0 = e0 / sum, wt1 = e1 / sum;
+    // reference point of this query (encoder.py:78-89) and sampling locations (:224-229)
+    const float fw = (float)bev_w, fh = (float)bev_h;
+    const float rx = __fdiv_rn((float)(q % bev_w) + 0.5f, fw);
+    const float ry = __fdiv_rn((float)(q / bev_w) + 0.5f, fh);
+    const float wim0 = __fadd_rn(rx, __fdiv_rn(off.x, fw)) * fw - 0.5f;
+    const float him0 = __fadd_rn(ry, __fdiv_rn(off.y, fh)) * fh - 0.5f;
+    const float wim1 = __fadd_rn(rx, __fdiv_rn(off.z, fw)) * fw - 0.5f;
+    const float him1 = __fadd_rn(ry, __fdiv_rn(off.w, fh)) * fh - 0.5f;
+
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const int grp = lane & ~3;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {                            // owner sub-lane o holds samples (o>>1, (o&1)*2 + {0,1})
+        const int src = grp | o;
+        const float a_w = __shfl_sync(0xffffffffu, wim0, src), a_h = __shfl_sync(0xffffffffu, him0, src);
+        const float b_w = __shfl_sync(0xffffffffu, wim1, src), b_h = __shfl_sync(0xffffffffu, him1, src);
+        const float a_t = __shfl_sync(0xffffffffu, wt0, src), b_t = __shfl_sync(0xffffffffu, wt1, src);
+        const T* base = ((o >> 1) == 0 ? value_prev : value_cur) + head * 32 + s * 8;
+        bilinear_acc8<T>(base, bev_h, bev_w, 256, a_h, a_w, a_t, acc);
+        bilinear_acc8<T>(base, bev_h, bev_w, 256, b_h, b_w, b_t, acc);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= 0.5f;
+    store8(out + (int64_t)q * 256 + head * 32 + s * 8, acc);
+}
+
+// ------------------------------------------------------------------------------------------
+// Camera projection of one pillar point (encoder.py:104-139), fp32, same operation order.
+__device__ __forceinline__ void project_point(const float* __restrict__ m /*4x4 row-major*/, float xs, float ys,
+                                              float zs, const ScaParams& sp, float& u, float& v, bool& ok)
+{
+    const float X = __fadd_rn(__fmul_rn(xs, sp.pc_scale[0]), sp.pc_min[0]);
+    const float Y = __fadd_rn(__fmul_rn(ys, sp.pc_scale[1]), sp.pc_min[1]);
+    const float Z = __fadd_rn(__fmul_rn(zs, sp.pc_scale[2]), sp.pc_min[2]);
+    const float cx = fmaf(m[2], Z, fmaf(m[1], Y, fmaf(m[0], X, m[3])));
+    const float cy = fmaf(m[6], Z, fmaf(m[5], Y, fmaf(m[4], X, m[7])));
+    const float cz = fmaf(m[10], Z, fmaf(m[9], Y, fmaf(m[8], X, m[11])));
+    const float eps = 1e-5f;
+    const float d = fmaxf(cz, eps);
+    u = __fdiv_rn(__fdiv_rn(cx, d), sp.img_w);
+    v = __fdiv_rn(__fdiv_rn(cy, d), sp.img_h);
+    ok = (cz > eps) && (v > 0.f) && (v < 1.f) && (u < 1.f) && (u > 0.f);
+}
+
+// debug / parity kernel for row a2: writes reference_points_cam [cam,Nq,D,2] and bev_mask [cam,Nq,D]
+__global__ void project_pillars_kernel(ScaParams sp, float* __restrict__ ref_cam, uint8_t* __restrict__ mask)
+{
+    const int Nq = sp.bev_h * sp.bev_w;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)sp.num_cams * Nq * sp.D) return;
+    const int z = (int)(idx % sp.D);
+    const int q = (int)((idx / sp.D) % Nq);
+    const int c = (int)(idx / ((int64_t)sp.D * Nq));
+    const float xs = __fdiv_rn((float)(q % sp.bev_w) + 0.5f, (float)sp.bev_w);
+    const float ys = __fdiv_rn((float)(q / sp.bev_w) + 0.5f, (float)sp.bev_h);
+    float u, v; bool ok;
+    project_point(sp.cam_mat[c], xs, ys, sp.zs[z], sp, u, v, ok);
+    ref_cam[idx * 2] = u; ref_cam[idx * 2 + 1] = v;
+    mask[idx] = ok ? 1 : 0;
+}
+
+// Fused spatial cross-attention gather (see file header).
+//   value [num_cams, Nv, 8, 32] T;  qproj [Nq, 768] f32 = [offsets (head,level,point,xy) | logits (head, level*point)]
+//   out  [Nq, 256] T  = sum_{visible cams} MSDA_cam(q) / max(1, #visible cams)
+//   hits (optional) [Nq] u8 = #visible cams (for tests / statistics)
+template <typename T>
+__global__ void __launch_bounds__(256)
+sca_fused_kernel(const T* __restrict__ value, const float* __restrict__ qproj, ScaParams sp, LevelGeom lg,
+                 int Nv, T* __restrict__ out, uint8_t* __restrict__ hits)
+{
+    const int Nq = sp.bev_h * sp.bev_w;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= Nq) return;
+    const int lane = threadIdx.x & 31, head = lane >> 2, s = lane & 3;   // s doubles as the owned level
+    const unsigned FULL = 0xffffffffu;
+
+    // ---- camera projection of the pillar: lane -> (cam = 4*round + lane/8, anchor = lane%8)
+    const float xs = __fdiv_rn((float)(q % sp.bev_w) + 0.5f, (float)sp.bev_w);
+    const float ys = __fdiv_rn((float)(q / sp.bev_w) + 0.5f, (float)sp.bev_h);
+    float ru[2], rv[2];
+    unsigned vis = 0;                                                    // bit c: camera c sees the pillar
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int c = r * 4 + (lane >> 3), z = lane & 7;
+        bool ok = false;
+        ru[r] = 0.f; rv[r] = 0.f;
+        if (c < sp.num_cams && z < sp.D) project_point(sp.cam_mat[c], xs, ys, sp.zs[z], sp, ru[r], rv[r], ok);
+        const unsigned b = __ballot_sync(FULL, ok);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if ((b >> (8 * k)) & 0xffu) vis |= 1u << (r * 4 + k);
+    }
+    const int count = __popc(vis);
+    if (hits && lane == 0) hits[q] = (uint8_t)count;
+
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+
+    if (count > 0) {
+        // ---- owner lane (head, level = s): 8 points x (dx, dy) and 8 logits
+        const float* qp = qproj + (int64_t)q * 768;
+        float offn[16], wl[8];
+        {
+            const float4* o4 = reinterpret_cast<const float4*>(qp + head * 64 + s * 16);
+            const float fw = (float)lg.w[s], fh = (float)lg.h[s];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 t = __ldg(o4 + i);
+                offn[4 * i + 0] = __fdiv_rn(t.x, fw); offn[4 * i + 1] = __fdiv_rn(t.y, fh);
+                offn[4 * i + 2] = __fdiv_rn(t.z, fw); offn[4 * i + 3] = __fdiv_rn(t.w, fh);
+            }
+            const float4* l4 = reinterpret_cast<const float4*>(qp + 512 + head * 32 + s * 8);
+            const float4 a = __ldg(l4), b = __ldg(l4 + 1);
+            wl[0] = a.x; wl[1] = a.y; wl[2] = a.z; wl[3] = a.w; wl[4] = b.x; wl[5] = b.y; wl[6] = b.z; wl[7] = b.w;
+            // softmax over the head's 32 logits = 4 lanes x 8 (spatial_cross_attention.py:343)
+            float mx = wl[0];
+#pragma unroll
+            for (int i = 1; i < 8; ++i) mx = fmaxf(mx, wl[i]);
+            mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 2));
+            float sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { wl[i] = expf(wl[i] - mx); sum += wl[i]; }
+            sum += __shfl_xor_sync(FULL, sum, 1);
+            sum += __shfl_xor_sync(FULL, sum, 2);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) wl[i] = wl[i] / sum;
+        }
+        const float own_w = (float)lg.w[s], own_h = (float)lg.h[s];
+        const int grp = lane & ~3;
+        for (int c = 0; c < sp.num_cams; ++c) {
+            if (!((vis >> c) & 1u)) continue;                            // warp-uniform
+            const int r = c >> 2;
+            // sampling location of point p uses pillar anchor p % D (Z-anchor interleave, :366-373)
+            float wim[8], him[8];
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                const int src = (c & 3) * 8 + (p % sp.D);
+                const float u = __shfl_sync(FULL, r ? ru[1] : ru[0], src);
+                const float v = __shfl_sync(FULL, r ? rv[1] : rv[0], src);
+                wim[p] = __fadd_rn(u, offn[2 * p]) * own_w - 0.5f;
+                him[p] = __fadd_rn(v, offn[2 * p + 1]) * own_h - 0.5f;
+            }
+            const T* vcam = value + ((int64_t)c * Nv * 8 + head) * 32 + s * 8;
+            for (int l = 0; l < 4; ++l) {
+                const int src = grp | l;
+                const T* base = vcam + (int64_t)lg.start[l] * 256;
+                const int H = lg.h[l], W = lg.w[l];
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    const float w_im = __shfl_sync(FULL, wim[p], src);
+                    const float h_im = __shfl_sync(FULL, him[p], src);
+                    const float wt = __shfl_sync(FULL, wl[p], src);
+                    bilinear_acc8<T>(base, H, W, 256, h_im, w_im, wt, acc);
+                }
+            }
+        }
+        const float cnt = (float)count;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = __fdiv_rn(acc[i], cnt);
+    }
+    store8(out + (int64_t)q * 256 + head * 32 + s * 8, acc);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ launchers
+int launch_msda_forward(const float* value, const int64_t* shapes, const int64_t* lstart, const float* loc,
+                        const float* wts, int B, int Nv, int M, int C, int Nq, int L, int P, float* out,
+                        cudaStream_t stream)
+{
+    if ((int64_t)B * Nq == 0) return 0;
+    if (C % 8 == 0) {
+        const int64_t total = (int64_t)B * Nq * M * (C / 8);
+        msda_forward_kernel<8><<<ceil_div(total, 256), 256, 0, stream>>>(value, shapes, lstart, loc, wts, B, Nv, M,
+                                                                          C, Nq, L, P, out);
+    } else {
+        const int64_t total = (int64_t)B * Nq * M * C;
+        msda_forward_kernel<1><<<ceil_div(total, 256), 256, 0, stream>>>(value, shapes, lstart, loc, wts, B, Nv, M,
+                                                                          C, Nq, L, P, out);
+    }
+    OCC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+int launch_tsa_fused(const T* value_prev, const T* value_cur, const float* qproj, int bev_h, int bev_w, T* out,
+                     cudaStream_t stream)
+{
+    const int Nq = bev_h * bev_w;
+    tsa_fused_kernel<T><<<ceil_div(Nq, 8), 256, 0, stream>>>(value_prev, value_cur, qproj, bev_h, bev_w, out);
+    OCC_CUDA(cudaGetLastError());
+    return 0;
+}
+template int launch_tsa_fused<float>(const float*, const float*, const float*, int, int, float*, cudaStream_t);
+template int launch_tsa_fused<bf16>(const bf16*, const bf16*, const float*, int, int, bf16*, cudaStream_t);
+
+template <typename T>
+int launch_sca_fused(const T* value, const float* qproj, const ScaParams& sp, const LevelGeom& lg, int Nv, T* out,
+                     uint8_t* hits, cudaStream_t stream)
+{
+    OCC_CHECK(lg.num_levels == 4 && sp.num_cams <= 8 && sp.D <= 8 && sp.D >= 1 && 8 % sp.D == 0,
+              "sca_fused: supports 4 levels, <= 8 cameras, pillar anchors in {1,2,4,8}");
+    const int Nq = sp.bev_h * sp.bev_w;
+    sca_fused_kernel<T><<<ceil_div(Nq, 8), 256, 0, stream>>>(value, qproj, sp, lg, Nv, out, hits);
+    OCC_CUDA(cudaGetLastError());
+    return 0;
+}
+template int launch_sca_fused<float>(const float*, const float*, const ScaParams&, const LevelGeom&, int, float*,
+                                     uint8_t*, cudaStream_t);
+template int launch_sca_fused<bf16>(const bf16*, const float*, const ScaParams&, const LevelGeom&, int, bf16*,
+                                    uint8_t*, cudaStream_t);
+
+int launch_project_pillars(const ScaParams& sp, float* ref_cam, uint8_t* mask, cudaStream_t stream)
+{
+    const int64_t total = (int64_t)sp.num_cams * sp.bev_h * sp.bev_w * sp.D;
+    project_pillars_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(sp, ref_cam, mask);
+    OCC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace occ

@@ -356,70 +356,6 @@ def get_occ(preds):
     return occ_score, preds['flow']
 
 
-# ------------------------------------------------------------------ parameter construction (reference init rules)
-def init_params(cfg, seed=2, perturb=True, num_embed_levels=None):
-    """Reference `init_weights` (spatial_cross_attention.py:253-271, temporal_self_attention.py:107-126,
-    transformer_occ.py:154-167) followed by the SURVEY 8d perturbation so that offsets / weights are
-    query-dependent (the stock init zeroes `sampling_offsets.weight` and `attention_weights.weight`)."""
-    g = torch.Generator().manual_seed(seed)
-    C = cfg['embed_dims']; M = cfg['num_heads']; L = cfg['num_levels']; P = cfg['sca_points']
-    Pt = cfg['tsa_points']; Q = cfg['num_bev_queue']; F_ = cfg['ffn_dim']
-    p = {}
-
-    def xavier(o, i):
-        a = math.sqrt(6.0 / (i + o))
-        return (torch.rand(o, i, generator=g) * 2 - 1) * a
-
-    def grid_bias(levels, points):
-        thetas = torch.arange(M, dtype=torch.float32) * (2.0 * math.pi / M)
-        gi = torch.stack([thetas.cos(), thetas.sin()], -1)
-        gi = (gi / gi.abs().max(-1, keepdim=True)[0]).view(M, 1, 1, 2).repeat(1, levels, points, 1)
-        for i in range(points):
-            gi[:, :, i, :] *= i + 1
-        return gi.reshape(-1)
-
-    Nq = cfg['bev_h'] * cfg['bev_w']
-    p['bev_embedding.weight'] = torch.randn(Nq, C, generator=g)
-    p['positional_encoding.row_embed.weight'] = torch.rand(cfg['bev_h'], C // 2, generator=g)
-    p['positional_encoding.col_embed.weight'] = torch.rand(cfg['bev_w'], C // 2, generator=g)
-    p['transformer.level_embeds'] = torch.randn(L, C, generator=g)
-    p['transformer.cams_embeds'] = torch.randn(cfg['num_cams'], C, generator=g)
-    for l in range(cfg['num_layers']):
-        pre = f'transformer.encoder.layers.{l}'
-        a0 = pre + '.attentions.0'
-        p[a0 + '.sampling_offsets.weight'] = torch.randn(Q * M * 1 * Pt * 2, C * Q, generator=g) * (0.02 if perturb else 0)
-        p[a0 + '.sampling_offsets.bias'] = grid_bias(1 * Q, Pt)
-        p[a0 + '.attention_weights.weight'] = torch.randn(Q * M * 1 * Pt, C * Q, generator=g) * (0.1 if perturb else 0)
-        p[a0 + '.attention_weights.bias'] = torch.zeros(Q * M * 1 * Pt)
-        p[a0 + '.value_proj.weight'] = xavier(C, C); p[a0 + '.value_proj.bias'] = torch.zeros(C)
-        p[a0 + '.output_proj.weight'] = xavier(C, C); p[a0 + '.output_proj.bias'] = torch.zeros(C)
-        a1 = pre + '.attentions.1'
-        d = a1 + '.deformable_attention'
-        p[d + '.sampling_offsets.weight'] = torch.randn(M * L * P * 2, C, generator=g) * (0.02 if perturb else 0)
-        p[d + '.sampling_offsets.bias'] = grid_bias(L, P)
-        p[d + '.attention_weights.weight'] = torch.randn(M * L * P, C, generator=g) * (0.1 if perturb else 0)
-        p[d + '.attention_weights.bias'] = torch.zeros(M * L * P)
-        p[d + '.value_proj.weight'] = xavier(C, C); p[d + '.value_proj.bias'] = torch.zeros(C)
-        p[a1 + '.output_proj.weight'] = xavier(C, C); p[a1 + '.output_proj.bias'] = torch.zeros(C)
-        f = pre + '.ffns.0'
-        p[f + '.layers.0.0.weight'] = xavier(F_, C); p[f + '.layers.0.0.bias'] = torch.randn(F_, generator=g) * 0.02
-        p[f + '.layers.1.weight'] = xavier(C, F_); p[f + '.layers.1.bias'] = torch.randn(C, generator=g) * 0.02
-        for n in range(3):
-            p[f'{pre}.norms.{n}.weight'] = 1 + 0.1 * torch.randn(C, generator=g) if perturb else torch.ones(C)
-            p[f'{pre}.norms.{n}.bias'] = 0.1 * torch.randn(C, generator=g) if perturb else torch.zeros(C)
-    mid = C // cfg['pillar_h']; od = cfg['out_dim']
-    for i, cin in enumerate((mid, od)):
-        pre = f'transformer.decoder.{i}'
-        fan = cin * 27
-        p[pre + '.conv.weight'] = torch.randn(od, cin, 3, 3, 3, generator=g) * math.sqrt(2.0 / fan)
-        p[pre + '.bn.weight'] = 1 + 0.1 * torch.randn(od, generator=g) if perturb else torch.ones(od)
-        p[pre + '.bn.bias'] = 0.1 * torch.randn(od, generator=g) if perturb else torch.zeros(od)
-        p[pre + '.bn.running_mean'] = 0.1 * torch.randn(od, generator=g) if perturb else torch.zeros(od)
-        p[pre + '.bn.running_var'] = 0.5 + torch.rand(od, generator=g) if perturb else torch.ones(od)
-        p[pre + '.bn.num_batches_tracked'] = torch.zeros((), dtype=torch.long)
-    for name, out in (('predicter', cfg['num_classes']), ('flow_predicter', 2)):
-        p[f'transformer.{name}.0.weight'] = xavier(od * 2, od)
-        p[f'transformer.{name}.0.bias'] = torch.randn(od * 2, generator=g) * 0.05
-        p[f'transformer.{name}.2.weight'] = xavier(out, od * 2)
-        p[f'transformer.{name}.2.bias'] = torch.randn(out, generator=g) * 0.05
-    return p
+# ------------------------------------------------------------------ parameter construction
+# Seeded synthetic weights are a fixture shared with the product-side benchmark: see occnet_b200/fixtures.py.
+from occnet_b200.fixtures import init_params  # noqa: E402,F401

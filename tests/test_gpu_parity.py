@@ -1,0 +1,407 @@
+"""GPU parity suite (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs, against the committed reference goldens, and through size-independent properties
+at full size.  Tolerances (stated per test): fp32 configuration 1e-3 absolute (BASELINE.json north_star),
+integer / index outputs bit-exact; the bf16 configuration has no reference counterpart (the reference
+is fp32-only) and carries its own stated tolerance."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from occnet_b200 import fixtures
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEV = 'cuda:0'
+
+
+def _oracle():
+    from oracle import bevformer_occ as O
+    from oracle import msda as OM
+    from oracle import ray_metrics as ORM
+    return O, OM, ORM
+
+
+def make_case(base, bs=1, with_prev=False, ang=None, **kw):
+    O, _, _ = _oracle()
+    cfg = fixtures.make_cfg(base, **kw)
+    params = O.init_params(cfg, seed=2)
+    feats = fixtures.make_feats(cfg, bs=bs, seed=1)
+    metas = fixtures.make_img_metas(cfg, bs=bs, can_bus_angle=ang)
+    prev = None
+    if with_prev:
+        g = torch.Generator().manual_seed(3)
+        prev = torch.randn(bs, cfg['bev_h'] * cfg['bev_w'], cfg['embed_dims'], generator=g)
+    return cfg, params, feats, metas, prev
+
+
+def engine_for(cfg, params, metas, precision='fp32', tc=False):
+    from occnet_b200.engine import OccEngine
+    eng = OccEngine(cfg, params, precision=precision, use_tensor_cores=tc, device=DEV)
+    eng.set_cameras(metas)
+    return eng
+
+
+def to_ref_layout(out, cfg):
+    """engine outputs -> reference tensor layouts (batch dim added)."""
+    C = cfg['embed_dims']
+    bev = out['bev_embed'].t().reshape(1, C, cfg['bev_h'], cfg['bev_w'])
+    return bev, out['occ'][None], out['flow'][None]
+
+
+# ------------------------------------------------------------------------------------------ operator boundary (a8)
+@pytest.mark.parametrize('shape', [
+    dict(B=2, M=8, C=32, Nq=300, levels=[(12, 20), (6, 10), (3, 5), (2, 3)], P=8),      # SCA-like
+    dict(B=2, M=8, C=32, Nq=625, levels=[(25, 25)], P=4),                               # TSA-like
+    dict(B=1, M=4, C=12, Nq=33, levels=[(5, 7), (3, 3)], P=3),                          # C % 8 != 0 -> scalar path
+    dict(B=3, M=2, C=8, Nq=0, levels=[(4, 4)], P=2),                                    # empty query set
+])
+def test_ms_deform_attn_forward_matches_oracle(shape):
+    from occnet_b200 import ops
+    _, OM, _ = _oracle()
+    torch.manual_seed(0)
+    shapes = torch.tensor(shape['levels'])
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    Nv = int(shapes.prod(1).sum())
+    B, M, C, Nq, P, L = shape['B'], shape['M'], shape['C'], shape['Nq'], shape['P'], len(shape['levels'])
+    value = torch.randn(B, Nv, M, C)
+    loc = torch.rand(B, Nq, M, L, P, 2) * 1.5 - 0.25      # includes out-of-image samples
+    if Nq > 4:                                            # exact borders / pixel centres
+        loc[0, 0] = 0.0; loc[0, 1] = 1.0; loc[0, 2] = 0.5
+        loc[0, 3, :, :, :, 0] = (torch.arange(P).float() + 0.5)[None, None] / shapes[:, 1].float()[None, :, None]
+    w = torch.rand(B, Nq, M, L, P)
+    got = ops.ms_deform_attn_forward(value.to(DEV), shapes.to(DEV), lsi.to(DEV), loc.to(DEV), w.to(DEV), 64).cpu()
+    if Nq == 0:
+        assert got.shape == (B, 0, M * C)
+        return
+    want = OM.msda_grid_sample(value, shapes, loc, w)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), atol=1e-4, rtol=0)          # bound 1e-3; observed ~1e-6
+    small = OM.msda_loops(value[:1, :, :, :], shapes, lsi, loc[:1, :8], w[:1, :8])
+    np.testing.assert_allclose(got[:1, :8].numpy(), small.numpy(), atol=2e-5, rtol=0)
+
+
+def test_ms_deform_attn_forward_error_behaviour():
+    from occnet_b200 import ops, _lib
+    v = torch.zeros(3, 16, 1, 8, device=DEV)
+    sh = torch.tensor([[4, 4]], device=DEV); ls = torch.tensor([0], device=DEV)
+    loc = torch.zeros(3, 2, 1, 1, 1, 2, device=DEV); w = torch.zeros(3, 2, 1, 1, 1, device=DEV)
+    with pytest.raises(_lib.OccB200Error):                       # mmcv: batch must divide im2col_step
+        ops.ms_deform_attn_forward(v, sh, ls, loc, w, 2)
+    with pytest.raises(RuntimeError):                            # non-contiguous input
+        ops.ms_deform_attn_forward(v.transpose(0, 1).contiguous().transpose(0, 1), sh, ls, loc, w, 64)
+    with pytest.raises(RuntimeError):                            # CPU tensor
+        ops.ms_deform_attn_forward(v.cpu(), sh, ls, loc, w, 64)
+    fn = ops.MultiScaleDeformableAttnFunction_fp32.apply(v, sh, ls, loc, w, 64)
+    assert fn.shape == (3, 2, 8)
+
+
+# ------------------------------------------------------------------------------------------ projection (a1, a2)
+@pytest.mark.parametrize('base', ['small6', 'full'])
+def test_pillar_projection_matches_point_sampling(base):
+    O, _, _ = _oracle()
+    cfg, params, feats, metas, _ = make_case(base, num_layers=1)
+    eng = engine_for(cfg, params, metas)
+    ref, mask = eng.project_pillars()
+    pc = cfg['pc_range']
+    ref_3d = O.get_reference_points(cfg['bev_h'], cfg['bev_w'], pc[5] - pc[2], cfg['num_points_in_pillar'], '3d', 1)
+    rpc, m = O.point_sampling(ref_3d, pc, metas)                 # (cam, B, Nq, D, 2), (cam, B, Nq, D)
+    flips = (mask.cpu().bool() != m[:, 0]).sum().item()
+    assert flips == 0, f'{flips} visibility flips'               # index-like output: exact
+    vis = m[:, 0]
+    d = (ref.cpu() - rpc[:, 0]).abs()[vis]
+    assert d.max().item() < 1e-5                                 # normalised image coords of visible points
+
+
+# ------------------------------------------------------------------------------------------ full path, fp32 config
+def _check_fp32(cfg, params, feats, metas, prev, per_layer=True):
+    O, _, _ = _oracle()
+    taps = {}
+    with torch.no_grad():
+        want = O.head_forward(params, cfg, feats, metas, prev_bev=None if prev is None else prev.clone(), taps=taps)
+    eng = engine_for(cfg, params, metas, 'fp32')
+    eng.enable_taps(True)
+    pb = None
+    if prev is not None:
+        pb = prev.clone()
+        if 'can_bus' in metas[0]:                                # the plugin rotates prev_bev before the engine (a9)
+            pb = O.rotate_prev_bev(pb[0], cfg['bev_h'], cfg['bev_w'], metas[0]['can_bus'][-1],
+                                   cfg.get('rotate_center', [100, 100]))[None]
+    out = eng.forward([f[0].to(DEV) for f in feats], prev_bev=pb,
+                      want=('bev_embed', 'occ', 'flow', 'occ_cls', 'occ_cls_i64'))
+    torch.cuda.synchronize()
+    if per_layer:
+        for l in range(cfg['num_layers']):
+            for name in ('tsa', 'sca', 'layer'):
+                key = f'layer{l}' + ('' if name == 'layer' else '_' + name)
+                err = (eng.tap(name, l).cpu() - taps[key][0]).abs().max().item()
+                assert err < 1e-3, f'layer {l} {name}: {err}'
+    bev, occ, flow = to_ref_layout({k: v.cpu() for k, v in out.items()}, cfg)
+    assert (bev - want['bev_embed']).abs().max().item() < 1e-3
+    assert (eng.tap('voxel').cpu()[None] - taps['voxel_feats']).abs().max().item() < 1e-3
+    assert (occ - want['occ']).abs().max().item() < 1e-3
+    assert (flow - want['flow']).abs().max().item() < 1e-3
+    cls_want = want['occ'].softmax(-1).argmax(-1)[0]
+    agree = (out['occ_cls'].cpu().long() == cls_want).float().mean().item()
+    assert agree > 0.9995                                        # ties within 1e-3 may flip
+    assert torch.equal(out['occ_cls'].cpu().long(), out['occ_cls_i64'].cpu())
+    assert torch.equal(out['occ_cls_i64'].cpu(), out['occ'].cpu().argmax(-1))          # indexing: exact vs own logits
+    return eng, out, want
+
+
+def test_engine_fp32_toy_cfg1():
+    _check_fp32(*make_case('toy'))
+
+
+def test_engine_fp32_small6_two_layers():
+    _check_fp32(*make_case('small6'))
+
+
+def test_engine_fp32_temporal_prev_bev():
+    _check_fp32(*make_case('small6', with_prev=True, ang=3.0, rotate_center=[20, 20]))
+
+
+@pytest.mark.parametrize('name', ['toy', 'small6', 'small6_prev'])
+def test_engine_fp32_matches_reference_golden(name, golden_dir):
+    """Against fixtures produced by the UNMODIFIED reference modules (tests/golden/gen_golden.py)."""
+    O, _, _ = _oracle()
+    spec = {'toy': ('toy', False, None, {}), 'small6': ('small6', False, None, {}),
+            'small6_prev': ('small6', True, 3.0, dict(rotate_center=[20, 20]))}[name]
+    cfg, params, feats, metas, prev = make_case(spec[0], with_prev=spec[1], ang=spec[2], **spec[3])
+    eng = engine_for(cfg, params, metas, 'fp32')
+    pb = None
+    if prev is not None:
+        pb = O.rotate_prev_bev(prev[0].clone(), cfg['bev_h'], cfg['bev_w'], 3.0, cfg['rotate_center'])[None]
+    out = eng.forward([f[0].to(DEV) for f in feats], prev_bev=pb)
+    bev, occ, flow = to_ref_layout({k: v.cpu() for k, v in out.items()}, cfg)
+    g = np.load(os.path.join(golden_dir, f'ref_model_{name}.npz'))
+    for k, t in (('bev_embed', bev), ('occ', occ), ('flow', flow)):
+        assert tuple(t.shape) == tuple(g[k + '_shape'])
+        sub = t.reshape(-1)[torch.from_numpy(g[k + '_idx'])].numpy()
+        np.testing.assert_allclose(sub, g[k + '_sub'], atol=1e-3, rtol=0)
+    assert (out['occ_cls'].cpu().numpy() == g['occ_cls'][0]).mean() > 0.9995
+
+
+def test_engine_fp32_full_size_one_layer():
+    """BASELINE configs[1] geometry (6 x 928x1600 -> 200x200 BEV, 200x200x16 voxels), one layer against the oracle."""
+    _check_fp32(*make_case('full', num_layers=1), per_layer=True)
+
+
+def test_engine_missing_parameter_is_loud():
+    from occnet_b200.engine import OccEngine
+    from occnet_b200 import _lib
+    cfg, params, *_ = make_case('toy')
+    bad = dict(params)
+    bad.pop('transformer.encoder.layers.0.attentions.1.output_proj.weight')
+    with pytest.raises(_lib.OccB200Error, match='missing parameter'):
+        OccEngine(cfg, bad, 'fp32', device=DEV)
+    with pytest.raises(_lib.OccB200Error, match='unknown parameter key'):
+        OccEngine(cfg, dict(params, **{'img_backbone.conv1.weight': torch.zeros(3)}), 'fp32', device=DEV)
+
+
+# ------------------------------------------------------------------------------------------ bf16 configuration
+def _check_bf16(tc):
+    O, _, _ = _oracle()
+    cfg, params, feats, metas, _ = make_case('small6')
+    with torch.no_grad():
+        want = O.head_forward(params, cfg, feats, metas)
+    eng = engine_for(cfg, params, metas, 'bf16', tc=tc)
+    out = eng.forward([f[0].to(DEV) for f in feats])
+    torch.cuda.synchronize()
+    bev, occ, flow = to_ref_layout({k: v.cpu() for k, v in out.items()}, cfg)
+    # bf16 storage (8-bit mantissa) of values / activations, fp32 accumulation: tolerance 6e-2 abs on O(1)
+    # LayerNorm outputs and logits, and >= 97 % argmax agreement with the fp32 oracle.
+    assert (bev - want['bev_embed']).abs().max().item() < 6e-2
+    assert (bev - want['bev_embed']).abs().mean().item() < 6e-3
+    assert (occ - want['occ']).abs().max().item() < 6e-2
+    assert (flow - want['flow']).abs().max().item() < 6e-2
+    agree = (out['occ_cls'].cpu().long() == want['occ'].softmax(-1).argmax(-1)[0]).float().mean().item()
+    assert agree > 0.97, agree
+
+
+def test_engine_bf16_simt_gemm():
+    _check_bf16(tc=False)
+
+
+def _run_isolated(code, timeout=300):
+    """tcgen05 bring-up runs in a child process: a device fault there must not poison this session's context."""
+    r = subprocess.run([sys.executable, '-c', code], cwd=ROOT, capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, f'child failed ({r.returncode}):\n{r.stdout[-3000:]}\n{r.stderr[-3000:]}'
+    return r.stdout
+
+
+TC_GEMM_CODE = r'''
+import torch, ctypes
+from occnet_b200 import _lib
+lib = _lib.load()
+torch.manual_seed(0)
+for (M, N, K) in [(128, 256, 256), (1000, 192, 512), (40000, 256, 256), (4100, 768, 256), (333, 512, 256)]:
+    A = (torch.randn(M, K, device='cuda') * 0.5).bfloat16()
+    W = (torch.randn(N, K, device='cuda') * 0.1).bfloat16()
+    b = torch.randn(N, device='cuda')
+    C = torch.full((M, N), float('nan'), device='cuda')
+    _lib.check(lib.occb200_gemm_bf16_tc(_lib.ptr(A), _lib.ptr(W), _lib.ptr(b), _lib.ptr(C), M, N, K, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().t() + b
+    err = (C - ref).abs().max().item()
+    print('tcgen05 gemm', M, N, K, 'max err', err)
+    assert err < 2e-3, err
+print('OK')
+'''
+
+
+def test_tcgen05_gemm_matches_fp32_matmul():
+    """bf16 x bf16 -> fp32 on the tensor cores equals an fp32 matmul of the same bf16-rounded operands (exact
+    products, fp32 accumulation order aside): tolerance 2e-3 on |C| ~ 2."""
+    out = _run_isolated(TC_GEMM_CODE)
+    assert 'OK' in out
+
+
+def test_engine_bf16_tensor_cores():
+    code = ("import sys; sys.path.insert(0, 'tests'); import test_gpu_parity as t; t._check_bf16(tc=True); print('OK')")
+    assert 'OK' in _run_isolated(code)
+
+
+# ------------------------------------------------------------------------------------------ host-buffer entry (e2e call)
+def test_forward_host_equals_device_path():
+    cfg, params, feats, metas, _ = make_case('small6')
+    eng = engine_for(cfg, params, metas, 'fp32')
+    out = eng.forward([f[0].to(DEV) for f in feats], want=('flow', 'occ_cls_i64'))
+    host = [f[0].contiguous().pin_memory() for f in feats]
+    occ_h, flow_h = eng.forward_host(host)
+    assert occ_h.dtype == torch.int64 and not occ_h.is_cuda
+    assert torch.equal(occ_h, out['occ_cls_i64'].cpu())
+    assert torch.equal(flow_h, out['flow'].cpu())
+
+
+# ------------------------------------------------------------------------------------------ metric (a14, a15)
+def _metric_fixture():
+    sem_gt, flow_gt = fixtures.make_occ_scene(seed=4)
+    rng = np.random.RandomState(5)
+    sem_pred = np.roll(sem_gt, 1, axis=0).copy()
+    flip = rng.rand(*sem_pred.shape) < 0.03
+    sem_pred[flip] = rng.randint(0, 17, int(flip.sum())).astype(np.uint8)
+    flow_pred = (np.roll(flow_gt, 1, axis=0) + rng.normal(0, 0.5, flow_gt.shape)).astype(np.float32)
+    return sem_pred, flow_pred, sem_gt, flow_gt
+
+
+def test_render_forward_bit_exact_vs_oracle_dda():
+    from occnet_b200 import ops
+    _, _, ORM = _oracle()
+    sem_pred, _, _, _ = _metric_fixture()
+    rays = ORM.generate_lidar_rays()
+    occ = np.ascontiguousarray(np.where(sem_pred < 16, 1, 0).astype(np.float32).transpose(2, 1, 0))[None]
+    for origin in ([0.98, 0.0, 1.84], [-20.0, 3.0, 1.84], [500.0, 500.0, 50.0], [39.9, -39.9, 5.3]):
+        o = ((np.asarray(origin, np.float32) - np.float32([-40, -40, -1])) / np.float32(0.4)).astype(np.float32)
+        p = ((rays + np.asarray(origin, np.float32) - np.float32([-40, -40, -1])) / np.float32(0.4)).astype(np.float32)
+        ti = np.zeros(len(rays), np.float32); ti[::97] = -1.0     # padded points are skipped
+        want = ORM.render_forward(occ, o[None], p, ti)
+        got = ops.render_forward(torch.from_numpy(occ)[None].to(DEV), torch.from_numpy(o)[None, None].to(DEV),
+                                 torch.from_numpy(p)[None].to(DEV), torch.from_numpy(ti)[None].to(DEV),
+                                 [1, 16, 200, 200], 'test')
+        np.testing.assert_array_equal(got[2][0].cpu().numpy(), want[2])          # voxel indices: bit-exact
+        np.testing.assert_array_equal(got[0][0].cpu().numpy(), want[0])          # fp64 traversal -> identical fp32
+        np.testing.assert_array_equal(got[1][0].cpu().numpy(), want[1])
+
+
+def test_render_forward_vs_reference_kernel_if_built():
+    """oracle/_ref holds the reference's own dvr.cu compiled here from /root/reference (oracle/build_ref.py)."""
+    import glob
+    so = glob.glob(os.path.join(ROOT, 'oracle', '_ref', 'dvr_ref*.so'))
+    if not so:
+        pytest.skip('oracle/_ref not built in this snapshot')
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('dvr_ref', so[0])
+    dvr = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(dvr)
+    from occnet_b200 import ops
+    _, _, ORM = _oracle()
+    sem_pred, _, _, _ = _metric_fixture()
+    rays = ORM.generate_lidar_rays()
+    occ = torch.from_numpy(np.ascontiguousarray(np.where(sem_pred < 16, 1, 0).astype(np.float32).transpose(2, 1, 0)))
+    occ = occ[None, None].to(DEV)
+    for origin in ([0.98, 0.0, 1.84], [-20.0, 3.0, 1.84], [500.0, 500.0, 50.0]):
+        o = torch.tensor(origin) - torch.tensor([-40.0, -40.0, -1.0])
+        o = (o / 0.4).float()[None, None].to(DEV)
+        p = ((torch.from_numpy(rays) + torch.tensor(origin) - torch.tensor([-40.0, -40.0, -1.0])) / 0.4).float()[None].to(DEV)
+        ti = torch.zeros(1, rays.shape[0], device=DEV)
+        ref = dvr.render_forward(occ, o, p, ti, [1, 16, 200, 200], 'test')
+        got = ops.render_forward(occ, o, p, ti, [1, 16, 200, 200], 'test')
+        want = ORM.render_forward(occ[0].cpu().numpy(), o[0].cpu().numpy(), p[0].cpu().numpy(), ti[0].cpu().numpy())
+        for i in range(3):
+            assert torch.equal(ref[i], got[i]), f'output {i} differs from the reference kernel'
+        np.testing.assert_array_equal(ref[0][0].cpu().numpy(), want[0])           # pins the C oracle too
+        np.testing.assert_array_equal(ref[2][0].cpu().numpy(), want[2])
+
+
+@pytest.mark.parametrize('f64', [False, True])
+def test_ray_metric_counters_match_oracle(f64, golden_dir):
+    from occnet_b200 import metric
+    _, _, ORM = _oracle()
+    sem_pred, flow_pred, sem_gt, flow_gt = _metric_fixture()
+    T = 2 if not f64 else 3
+    orig = fixtures.make_ray_origins(T=T)
+    if f64:
+        orig = orig.astype(np.float64) + 1e-9
+    rm = metric.RayMetric(DEV)
+    pp, pg = rm.add_frame(torch.from_numpy(sem_pred), torch.from_numpy(flow_pred), torch.from_numpy(sem_gt),
+                          torch.from_numpy(flow_gt), torch.from_numpy(orig), return_pcd=True)
+    rays = ORM.generate_lidar_rays()
+    if f64:
+        # torch promotion semantics (float32 rays + float64 origins) restated with numpy float64
+        lid = rays[None].astype(np.float64) + orig[:, :, None, :].reshape(1, T, 1, 3)
+        want_p, want_g = [], []
+        off = np.float32([-40, -40, -1]).astype(np.float64); sc = np.float64(np.float32(0.4))
+        for t in range(T):
+            o = ((orig[0, t] - off) / sc).astype(np.float32)
+            p = ((lid[0, t] - off) / sc).astype(np.float32)
+            for sem, flow, dst in ((sem_pred, flow_pred, want_p), (sem_gt, flow_gt, want_g)):
+                occ = np.ascontiguousarray(np.where(sem < 16, 1, 0).astype(np.float32).transpose(2, 1, 0))[None]
+                pd, _, ci = ORM.render_forward(occ, o[None], p, np.zeros(len(rays), np.float32))
+                ci = ci.astype(np.int32)
+                dst.append(np.concatenate([sem[ci[:, 0], ci[:, 1], ci[:, 2]].astype(np.float32)[:, None],
+                                           (pd * np.float32(0.4))[:, None], flow[ci[:, 0], ci[:, 1], ci[:, 2]]], -1))
+        want_p = np.concatenate(want_p); want_g = np.concatenate(want_g)
+    else:
+        want_p = ORM.process_one_sample(sem_pred, rays, orig, flow_pred)
+        want_g = ORM.process_one_sample(sem_gt, rays, orig, flow_gt)
+    np.testing.assert_array_equal(pp.cpu().numpy(), want_p)                       # class, dist, flow rows: bit-exact
+    np.testing.assert_array_equal(pg.cpu().numpy(), want_g)
+    valid = want_g[:, 0].astype(np.int32) != 16
+    cnt = ORM.accumulate(ORM.new_counters(), want_p[valid], want_g[valid])
+    vec = ORM.counters_to_vector(cnt)
+    got = rm.counters.cpu().numpy()
+    n = 17
+    np.testing.assert_array_equal(got[:5 * n], vec[:5 * n])                        # integer counters: exact
+    np.testing.assert_array_equal(got[8 * n:], vec[8 * n:])
+    np.testing.assert_allclose(got[5 * n:8 * n], vec[5 * n:8 * n], rtol=1e-5)      # fp sums: order differs
+    fin = rm.finalize(); want = ORM.finalize(cnt)
+    assert abs(fin['miou'] - want['miou']) < 1e-12 and abs(fin['mave'] - want['mave']) < 1e-5
+    if not f64:
+        g = np.load(os.path.join(golden_dir, 'ref_metric.npz'))
+        np.testing.assert_array_equal(pp.cpu().numpy(), g['pcd_pred'])             # the reference's own output
+        np.testing.assert_allclose(fin['iou'], g['iou'], equal_nan=True, rtol=1e-12)
+    # empty: zero origins leaves the counters untouched
+    before = rm.counters.clone()
+    rm.add_frame(torch.from_numpy(sem_pred), torch.from_numpy(flow_pred), torch.from_numpy(sem_gt),
+                 torch.from_numpy(flow_gt), torch.zeros(0, 3))
+    assert torch.equal(before, rm.counters)
+
+
+def test_full_size_properties_bf16():
+    """BASELINE full sizes, size-independent properties: determinism (bit-identical reruns), argmax consistent with
+    the engine's own logits, per-query independence from unrelated camera content."""
+    cfg, params, feats, metas, _ = make_case('full', num_layers=2)
+    eng = engine_for(cfg, params, metas, 'bf16')
+    fd = [f[0].to(DEV) for f in feats]
+    a = eng.forward(fd, want=('bev_embed', 'occ', 'occ_cls', 'flow'))
+    a = {k: v.clone() for k, v in a.items()}
+    b = eng.forward(fd, want=('bev_embed', 'occ', 'occ_cls', 'flow'))
+    for k in a:
+        assert torch.equal(a[k], b[k]), f'{k} not deterministic'
+    assert torch.equal(a['occ'].argmax(-1).to(torch.uint8), a['occ_cls'])
+    assert torch.isfinite(a['bev_embed']).all() and torch.isfinite(a['occ']).all()
+    assert eng.launches_per_frame > 20

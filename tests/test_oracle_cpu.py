@@ -1,0 +1,180 @@
+"""CPU suite (-m "not gpu"): the oracle against the committed goldens (generated from the unmodified
+reference modules by tests/golden/gen_golden.py), independent cross-checks, host logic, and the C ABI surface."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from occnet_b200 import fixtures
+from oracle import bevformer_occ as O
+from oracle import msda as OM
+from oracle import ray_metrics as ORM
+
+CASES = {
+    'toy': (fixtures.make_cfg('toy'), 1, False, None),
+    'small6': (fixtures.make_cfg('small6'), 1, False, None),
+    'small6_b2': (fixtures.make_cfg('small6', num_layers=1), 2, False, None),
+    'small6_prev': (fixtures.make_cfg('small6', rotate_center=[20, 20]), 1, True, 3.0),
+}
+
+
+def run_oracle_case(name):
+    cfg, bs, with_prev, ang = CASES[name]
+    params = O.init_params(cfg, seed=2)
+    feats = fixtures.make_feats(cfg, bs=bs, seed=1)
+    metas = fixtures.make_img_metas(cfg, bs=bs, can_bus_angle=ang)
+    prev = None
+    if with_prev:
+        g = torch.Generator().manual_seed(3)
+        prev = torch.randn(bs, cfg['bev_h'] * cfg['bev_w'], cfg['embed_dims'], generator=g)
+    with torch.no_grad():
+        out = O.head_forward(params, cfg, feats, metas, prev_bev=prev)
+    return cfg, out
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_oracle_matches_reference_golden(name, golden_dir):
+    """Oracle == unmodified reference modules (goldens), incl. batch-2 quirks and the temporal path."""
+    g = np.load(os.path.join(golden_dir, f'ref_model_{name}.npz'))
+    _, out = run_oracle_case(name)
+    for k in ('bev_embed', 'occ', 'flow'):
+        assert tuple(out[k].shape) == tuple(g[k + '_shape'])
+        sub = out[k].reshape(-1)[torch.from_numpy(g[k + '_idx'])].numpy()
+        np.testing.assert_allclose(sub, g[k + '_sub'], rtol=0, atol=2e-5)
+        assert abs(out[k].abs().double().mean().item() - float(g[k + '_absmean'])) < 1e-5
+    cls = out['occ'].softmax(-1).argmax(-1).numpy().astype(np.uint8)
+    assert (cls == g['occ_cls']).mean() > 0.9999
+
+
+def test_msda_three_way():
+    """grid_sample restatement == scalar CUDA-kernel formulation == transformers' independent implementation."""
+    torch.manual_seed(0)
+    B, M, C, L, P, Nq = 2, 4, 8, 3, 4, 37
+    shapes = torch.tensor([[7, 9], [4, 5], [2, 3]])
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    Nv = int(shapes.prod(1).sum())
+    value = torch.randn(B, Nv, M, C)
+    loc = torch.rand(B, Nq, M, L, P, 2) * 1.4 - 0.2          # some samples fall outside the maps
+    w = torch.rand(B, Nq, M, L, P)
+    a = OM.msda_grid_sample(value, shapes, loc, w)
+    b = OM.msda_loops(value, shapes, lsi, loc, w)
+    np.testing.assert_allclose(a.numpy(), b.numpy(), atol=2e-5, rtol=0)
+    from transformers.models.mask2former.modeling_mask2former import multi_scale_deformable_attention
+    c = multi_scale_deformable_attention(value, [(int(h), int(wd)) for h, wd in shapes], loc, w)
+    np.testing.assert_allclose(a.numpy(), c.numpy(), atol=2e-5, rtol=0)
+
+
+def test_sca_rebatch_equals_direct_formula():
+    """the reference's rebatch is a memory optimisation; the fused per-(query,camera) sum is exact (B=1)."""
+    cfg = fixtures.make_cfg('small6')
+    p = O.init_params(cfg, seed=2)
+    feats = fixtures.make_feats(cfg, bs=1, seed=1)
+    metas = fixtures.make_img_metas(cfg, bs=1)
+    pc = cfg['pc_range']
+    Nq = cfg['bev_h'] * cfg['bev_w']
+    ref_3d = O.get_reference_points(cfg['bev_h'], cfg['bev_w'], pc[5] - pc[2], cfg['num_points_in_pillar'], '3d', 1)
+    rpc, mask = O.point_sampling(ref_3d, pc, metas)
+    value, shapes, lsi = O.pack_camera_features(p, 'transformer', cfg, feats)
+    q = torch.randn(1, Nq, 256, generator=torch.Generator().manual_seed(7))
+    pre = 'transformer.encoder.layers.0.attentions.1'
+    with torch.no_grad():
+        a = O.spatial_cross_attention(p, pre, cfg, q, value, value, rpc, mask, shapes, lsi)
+        b = O.spatial_cross_attention_direct(p, pre, cfg, q, value, rpc, mask, shapes, lsi)
+    assert mask.any() and (mask.sum(-1) > 0).sum() > 100
+    np.testing.assert_allclose(a.numpy(), b.numpy(), atol=1e-5, rtol=0)
+
+
+def test_reference_points_closed_form():
+    r3 = O.get_reference_points(4, 5, 6.4, 8, '3d', 1)
+    assert r3.shape == (1, 8, 20, 3)
+    np.testing.assert_allclose(r3[0, 0, :5, 0].numpy(), (np.arange(5) + 0.5) / 5, atol=1e-7)
+    np.testing.assert_allclose(r3[0, :, 0, 2].numpy(), np.linspace(0.5, 5.9, 8) / 6.4, atol=1e-6)
+    r2 = O.get_reference_points(4, 5, dim='2d', bs=1)
+    assert r2.shape == (1, 20, 1, 2)
+    np.testing.assert_allclose(r2[0, 7, 0].numpy(), [(7 % 5 + 0.5) / 5, (7 // 5 + 0.5) / 4], atol=1e-7)
+
+
+def test_rig_statistics_full_size():
+    """SURVEY 8d fixture numbers: visible queries per camera at 200x200, D=8, img (928,1600)."""
+    cfg = fixtures.make_cfg('full')
+    metas = fixtures.make_img_metas(cfg)
+    pc = cfg['pc_range']
+    ref_3d = O.get_reference_points(200, 200, pc[5] - pc[2], 8, '3d', 1)
+    _, mask = O.point_sampling(ref_3d, pc, metas)
+    per_cam = (mask[:, 0].sum(-1) > 0).sum(-1).tolist()
+    assert per_cam == [5790, 7339, 7334, 9893, 7148, 7090]
+
+
+def test_metric_oracle_matches_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'ref_metric.npz'))
+    rays = ORM.generate_lidar_rays()
+    assert rays.shape == (14040, 3)
+    np.testing.assert_array_equal(rays[:4], g['rays_first'])
+    np.testing.assert_array_equal(rays[-4:], g['rays_last'])
+    sem_gt, flow_gt = fixtures.make_occ_scene(seed=4)
+    rng = np.random.RandomState(5)
+    sem_pred = np.roll(sem_gt, 1, axis=0).copy()
+    flip = rng.rand(*sem_pred.shape) < 0.03
+    sem_pred[flip] = rng.randint(0, 17, int(flip.sum())).astype(np.uint8)
+    flow_pred = (np.roll(flow_gt, 1, axis=0) + rng.normal(0, 0.5, flow_gt.shape)).astype(np.float32)
+    orig = fixtures.make_ray_origins(T=2)
+    pp = ORM.process_one_sample(sem_pred, rays, orig, flow_pred)
+    pg = ORM.process_one_sample(sem_gt, rays, orig, flow_gt)
+    np.testing.assert_array_equal(pp, g['pcd_pred'])
+    np.testing.assert_array_equal(pg[:, 0].astype(np.uint8), g['pcd_gt_cls'])
+    np.testing.assert_array_equal(pg[:, 1], g['pcd_gt_dist'])
+    valid = pg[:, 0].astype(np.int32) != 16
+    cnt = ORM.accumulate(ORM.new_counters(), pp[valid], pg[valid])
+    np.testing.assert_allclose(ORM.counters_to_vector(cnt), g['counters'], rtol=1e-12)
+    fin = ORM.finalize(cnt)
+    np.testing.assert_allclose(fin['iou'], g['iou'], equal_nan=True)
+    np.testing.assert_allclose(fin['ave'], g['ave'], equal_nan=True)
+    # empty / degenerate: no origins -> no rays -> empty result; a ray bundle that never enters the grid
+    far = np.array([[[500.0, 500.0, 50.0]]], np.float32)
+    out = ORM.process_one_sample(sem_gt, rays[:16], far, flow_gt)
+    assert out.shape == (16, 4) and np.allclose(out[:, 1], -0.4) and (out[:, 0] == sem_gt[0, 0, 0]).all()
+
+
+def test_host_metric_finalize_matches_oracle(golden_dir):
+    from occnet_b200 import metric
+    g = np.load(os.path.join(golden_dir, 'ref_metric.npz'))
+    fin = metric.finalize_counters(g['counters'])
+    np.testing.assert_allclose(fin['iou'], g['iou'], equal_nan=True)
+    np.testing.assert_allclose(fin['ave'], g['ave'], equal_nan=True)
+    np.testing.assert_array_equal(metric.generate_lidar_rays(), ORM.generate_lidar_rays())
+
+
+def test_c_abi_exports_every_declared_symbol(lib_built):
+    import ctypes
+    from occnet_b200 import _lib
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'include', 'occ_b200.h')).read()
+    declared = set(re.findall(r'\b(occb200_\w+)\s*\(', hdr))
+    assert len(declared) >= 18
+    lib = ctypes.CDLL(lib_built)
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in include/occ_b200.h but not exported'
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert b'sm_100a' in _lib.load().occb200_version()
+
+
+def test_product_path_fails_loudly_without_gpu():
+    from occnet_b200 import ops
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    with pytest.raises(RuntimeError):
+        ops.ms_deform_attn_forward(torch.zeros(1, 4, 1, 8), torch.tensor([[2, 2]]), torch.tensor([0]),
+                                   torch.zeros(1, 1, 1, 1, 1, 2), torch.zeros(1, 1, 1, 1, 1))
+    from occnet_b200.engine import OccEngine
+    with pytest.raises(RuntimeError):
+        OccEngine(fixtures.make_cfg('toy'), {}, 'fp32')
+
+
+def test_no_oracle_import_in_product():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for d, _, files in os.walk(os.path.join(root, 'occnet_b200')):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh')):
+                src = open(os.path.join(d, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', src, re.M), f'{f} imports the oracle'
