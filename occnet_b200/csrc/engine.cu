@@ -293,8 +293,9 @@ int occb200_ms_deform_attn_forward(const float* value, const int64_t* spatial_sh
                                    const float* sampling_loc, const float* attn_weight, int B, int Nv, int M, int C,
                                    int Nq, int L, int P, int im2col_step, float* out, void* stream)
 {
-    OCC_CHECK(value && spatial_shapes && level_start_index && sampling_loc && attn_weight && out, "null pointer");
     OCC_CHECK(B >= 0 && Nv >= 0 && M > 0 && C > 0 && Nq >= 0 && L > 0 && P > 0, "bad sizes");
+    if ((int64_t)B * Nq == 0) return 0;                          // empty query set: nothing to write
+    OCC_CHECK(value && spatial_shapes && level_start_index && sampling_loc && attn_weight && out, "null pointer");
     const int step = im2col_step < B ? im2col_step : B;
     OCC_CHECK(B == 0 || (step > 0 && B % step == 0), "batch(" + std::to_string(B) + ") must divide im2col_step(" +
                                                          std::to_string(im2col_step) + ")");
@@ -624,6 +625,7 @@ int occb200_ray_metric_accumulate(const uint8_t* sem_pred, const float* flow_pre
                                   const float* flow_gt, const void* origins, int origin_is_f64, int T, const float* rays,
                                   int M, double* counters, float* pcd_pred, float* pcd_gt, void* stream)
 {
+    if (T == 0 || M == 0) return 0;                              // no origins / rays: counters untouched
     OCC_CHECK(sem_pred && flow_pred && sem_gt && flow_gt && origins && rays && counters, "null pointer");
     return launch_ray_metric(sem_pred, flow_pred, sem_gt, flow_gt, origins, origin_is_f64, T, rays, M, counters,
                              pcd_pred, pcd_gt, (cudaStream_t)stream);
