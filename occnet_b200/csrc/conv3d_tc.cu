@@ -1,0 +1,185 @@
+// Voxel decoder on the 5th-gen tensor cores (sm_100a): 3x3x3 Conv3d (pad 1, no bias) + folded
+// BatchNorm3d + ReLU as an implicit GEMM.   Reference: TransformerOcc.decoder (use_3d),
+// projects/mmdet3d_plugin/bevformer/modules/transformer_occ.py:106-131, applied at :305-308.
+//
+// Tensors are channels-last bf16 [X][Y][Z][C] (see decoder_simt.cu for the layout rationale).
+//   M tile  = 128 voxels = 8 (y) x 16 (z, the whole pillar) at one x
+//   N       = 32 output channels,  K = 27 taps x Cin
+// im2col is done by TMA: one 4-D box load {Cin, 16 z, 8 y, 1 x} per tap with the tap's (dz,dy,dx) offset
+// in the coordinates; out-of-bounds rows are zero-filled by the TMA unit, which IS the conv's zero padding
+// (including the z = -1 / z = 16 halo).  All 27 weight tiles stay resident in shared memory.
+//   warp 0: TMA producer (8-stage ring)    warp 1: tcgen05.mma issuer (accumulator double-buffered in TMEM)
+//   warps 2-5: epilogue (tcgen05.ld -> +bias -> ReLU -> bf16 -> 64-byte rows, contiguous 8 KB per tile)
+#include "common.cuh"
+#include "conv3d_tc.cuh"
+#include "tc_common.cuh"
+
+namespace occ {
+
+namespace {
+
+constexpr int STAGES = 8, TILE_Y = 8, TILE_Z = 16, BLOCK_M = 128, COUT = 32, TAPS = 27;
+constexpr int NUM_THREADS = 192;
+
+template <int CIN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
+                 const float* __restrict__ bias, bf16* __restrict__ out, int X, int Y)
+{
+    constexpr int ROW_BYTES = CIN * 2;                       // 32 (SWIZZLE_32B) or 64 (SWIZZLE_64B)
+    constexpr int A_BYTES = BLOCK_M * ROW_BYTES;             // 4 / 8 KB per stage
+    constexpr int W_TAP_BYTES = COUT * ROW_BYTES;            // 1 / 2 KB per tap
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t w_base = smem_base;                                       // 27 weight tiles, resident
+    const uint32_t a_base = smem_base + ((TAPS * W_TAP_BYTES + 1023) & ~1023);
+    const uint32_t bar_base = a_base + STAGES * A_BYTES;
+    auto full_bar = [&](int s) { return bar_base + s * 8; };
+    auto empty_bar = [&](int s) { return bar_base + (STAGES + s) * 8; };
+    auto tfull_bar = [&](int s) { return bar_base + (2 * STAGES + s) * 8; };
+    auto tempty_bar = [&](int s) { return bar_base + (2 * STAGES + 2 + s) * 8; };
+    const uint32_t w_bar = bar_base + (2 * STAGES + 4) * 8;
+    const uint32_t tmem_slot = bar_base + (2 * STAGES + 5) * 8;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int y_tiles = (Y + TILE_Y - 1) / TILE_Y;
+    const int num_tiles = X * y_tiles;
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmIn); tc::tma_prefetch_desc(&tmW);
+        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(full_bar(s), 1); tc::mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(tfull_bar(s), 1); tc::mbar_init(tempty_bar(s), 128); }
+        tc::mbar_init(w_bar, 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_slot, 64);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tc::mbar_arrive_expect_tx(w_bar, TAPS * W_TAP_BYTES);
+            for (int t = 0; t < TAPS; ++t) tc::tma_load_2d(w_base + t * W_TAP_BYTES, &tmW, w_bar, 0, t * COUT);
+            int s = 0; uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int x = tile / y_tiles, y0 = (tile % y_tiles) * TILE_Y;
+                for (int t = 0; t < TAPS; ++t) {
+                    const int dz = t / 9, dy = (t / 3) % 3, dx = t % 3;
+                    tc::mbar_wait(empty_bar(s), ph ^ 1);
+                    tc::mbar_arrive_expect_tx(full_bar(s), A_BYTES);
+                    tc::tma_load_4d(a_base + s * A_BYTES, &tmIn, full_bar(s), 0, dz - 1, y0 + dy - 1, x + dx - 1);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = tc::make_idesc_bf16(BLOCK_M, COUT);
+        int s = 0; uint32_t ph = 0; int as = 0; uint32_t aph = 0;
+        if (lane == 0) { tc::mbar_wait(w_bar, 0); tc::tc_fence_after(); }
+        __syncwarp();
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            if (lane == 0) { tc::mbar_wait(tempty_bar(as), aph ^ 1); tc::tc_fence_after(); }
+            __syncwarp();
+            for (int t = 0; t < TAPS; ++t) {
+                if (lane == 0) {
+                    tc::mbar_wait(full_bar(s), ph);
+                    tc::tc_fence_after();
+                    const uint64_t da = tc::make_smem_desc(a_base + s * A_BYTES, ROW_BYTES);
+                    const uint64_t db = tc::make_smem_desc(w_base + t * W_TAP_BYTES, ROW_BYTES);
+#pragma unroll
+                    for (int k = 0; k < CIN / 16; ++k)
+                        tc::umma_bf16(tmem_base + as * 32, da + 2 * k, db + 2 * k, idesc, (t | k) != 0);
+                    tc::umma_commit(empty_bar(s));
+                    if (t == TAPS - 1) tc::umma_commit(tfull_bar(as));
+                }
+                __syncwarp();
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+            if (++as == 2) { as = 0; aph ^= 1; }
+        }
+    } else {
+        const int quarter = warp & 3;
+        int as = 0; uint32_t aph = 0;
+        float b[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) b[i] = __ldg(bias + i);
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int x = tile / y_tiles, y0 = (tile % y_tiles) * TILE_Y;
+            tc::mbar_wait(tfull_bar(as), aph);
+            tc::tc_fence_after();
+            uint32_t r[32];
+            tc::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + as * 32, r);
+            tc::tmem_ld_wait();
+            tc::tc_fence_before();
+            tc::mbar_arrive(tempty_bar(as));                 // accumulator is in registers: release TMEM early
+            const int row = quarter * 32 + lane;
+            const int y = y0 + row / TILE_Z, z = row % TILE_Z;
+            if (y < Y) {
+                uint4* op = reinterpret_cast<uint4*>(out + ((((size_t)x * Y + y) * TILE_Z + z) * COUT));
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(r[8 * i + j]) + b[8 * i + j], 0.f);
+                    uint4 u;
+                    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+                    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+                    op[i] = u;
+                }
+            }
+            if (++as == 2) { as = 0; aph ^= 1; }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, 64);
+    }
+}
+
+}  // namespace
+
+int launch_conv3d_tc(const bf16* in, const bf16* w_tap_major, const float* bias, int X, int Y, int Z, int Cin,
+                     bf16* out, cudaStream_t stream)
+{
+    OCC_CHECK(Z == TILE_Z && (Cin == 16 || Cin == 32), "conv3d_tc: Z must be 16 and Cin in {16, 32}");
+    const int row_bytes = Cin * 2;
+    CUtensorMap tmIn, tmW;
+    {
+        const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Z, (uint64_t)Y, (uint64_t)X};
+        const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)Z * Cin * 2, (uint64_t)Y * Z * Cin * 2};
+        const uint32_t box[4] = {(uint32_t)Cin, (uint32_t)TILE_Z, (uint32_t)TILE_Y, 1u};
+        if (make_tensor_map_bf16(&tmIn, in, 4, dims, strides, box, row_bytes)) return 1;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)Cin, (uint64_t)TAPS * COUT};
+        const uint64_t strides[1] = {(uint64_t)Cin * 2};
+        const uint32_t box[2] = {(uint32_t)Cin, (uint32_t)COUT};
+        if (make_tensor_map_bf16(&tmW, w_tap_major, 2, dims, strides, box, row_bytes)) return 1;
+    }
+    const int a_bytes = BLOCK_M * row_bytes, w_bytes = (TAPS * COUT * row_bytes + 1023) & ~1023;
+    const int smem = 1024 + w_bytes + STAGES * a_bytes + 256;
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        OCC_CUDA(cudaGetDevice(&dev));
+        OCC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int tiles = X * ((Y + TILE_Y - 1) / TILE_Y);
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    if (Cin == 16) {
+        OCC_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        conv3d_tc_kernel<16><<<grid, NUM_THREADS, smem, stream>>>(tmIn, tmW, bias, out, X, Y);
+    } else {
+        OCC_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        conv3d_tc_kernel<32><<<grid, NUM_THREADS, smem, stream>>>(tmIn, tmW, bias, out, X, Y);
+    }
+    OCC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace occ

@@ -8,6 +8,7 @@
 //   bev_to_voxel, conv3d x2, occ_head                 transformer_occ.py:305-319, bevformer_occ_head.py:211-212
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -16,6 +17,7 @@
 
 #include "../../include/occ_b200.h"
 #include "common.cuh"
+#include "conv3d_tc.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 
@@ -64,7 +66,7 @@ struct occb200_engine {
     std::vector<LayerW> layers;
     DevBuf bev_queries, pos, cams_embeds, level_embeds;
     DevBuf conv_w[2], conv_b[2], conv_wh[2];
-    DevBuf hw1, hb1, hw2, hb2, fw1, fb1, fw2, fb2, head_wh;
+    DevBuf hw1, hb1, hw2, hb2, fw1, fb1, fw2, fb2, head_w1h, head_w2h, head_b1c, head_b2c;
     // workspace
     DevBuf tokens, sca_value, q_f32, q_t, q_pos_t, q0_t, prev_t, tsa_value, tsa_value_prev, qproj, attn_out, x_f32,
         ffn_h, vox0, vox1, vox2, hits;
@@ -150,6 +152,16 @@ int gemm(occb200_engine* e, const TA* A, const TA* A2, int K1, const float* W, c
     return gemm_simt<TA, TC>(A, lda, A2, A2 ? K - K1 : 0, K1, W, bias, residual, N, C, N, M, N, K, act, st);
 }
 
+// y = LayerNorm(A.W^T + b + residual): one tcgen05 kernel (GEMM with LayerNorm epilogue) on the tensor-core path
+int gemm_ln_fused(occb200_engine* e, const bf16* A, const void* Wh, const float* bias, const float* residual,
+                  const float* gamma, const float* beta, const float* pos, float* y_f32, bf16* y_t, bf16* y_pos_t, int M,
+                  int K, cudaStream_t st)
+{
+    e->launches++;
+    ProfScope ps(e, st, CAT_GEMM);
+    return gemm_tc_ln(A, reinterpret_cast<const bf16*>(Wh), bias, residual, gamma, beta, pos, y_f32, y_t, y_pos_t, M, K, st);
+}
+
 template <typename T>
 int forward_impl(occb200_engine* e, const float* const* feats, const float* prev_bev, float* bev_embed,
                  float* occ_logits, float* flow, uint8_t* cls_u8, int64_t* cls_i64, cudaStream_t st)
@@ -204,17 +216,24 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
             if (launch_tsa_fused<T>(v_prev, v_cur, qproj, c.bev_h, c.bev_w, attn_out, st)) return 2;
         }
         e->launches++;
-        if (gemm<T, float>(e, attn_out, nullptr, 0, w.tsa_o_w.as<float>(), w.tsa_o_wh.p, w.tsa_o_b.as<float>(), q_f32,
-                           x_f32, Nq, C, C, ACT_NONE, st)) return 2;
-        if (e->taps)
-            OCC_CUDA(cudaMemcpyAsync(e->tap_tsa.as<float>() + (size_t)l * Nq * C, x_f32, (size_t)Nq * C * 4,
-                                     cudaMemcpyDeviceToDevice, st));
-        {
-            ProfScope ps(e, st, CAT_LN);
-            if (launch_layernorm<T>(x_f32, w.ln_g[0].as<float>(), w.ln_b[0].as<float>(), nullptr, Nq, C, q_f32, q_t,
-                                    (T*)nullptr, st)) return 2;
+        const bool fuse_ln = sizeof(T) == 2 && c.use_tensor_cores && !e->taps && w.tsa_o_wh.p != nullptr;
+        if (fuse_ln) {
+            if (gemm_ln_fused(e, (const bf16*)attn_out, w.tsa_o_wh.p, w.tsa_o_b.as<float>(), q_f32, w.ln_g[0].as<float>(),
+                              w.ln_b[0].as<float>(), nullptr, x_f32, (bf16*)q_t, nullptr, Nq, C, st)) return 2;
+            std::swap(q_f32, x_f32);
+        } else {
+            if (gemm<T, float>(e, attn_out, nullptr, 0, w.tsa_o_w.as<float>(), w.tsa_o_wh.p, w.tsa_o_b.as<float>(),
+                               q_f32, x_f32, Nq, C, C, ACT_NONE, st)) return 2;
+            if (e->taps)
+                OCC_CUDA(cudaMemcpyAsync(e->tap_tsa.as<float>() + (size_t)l * Nq * C, x_f32, (size_t)Nq * C * 4,
+                                         cudaMemcpyDeviceToDevice, st));
+            {
+                ProfScope ps(e, st, CAT_LN);
+                if (launch_layernorm<T>(x_f32, w.ln_g[0].as<float>(), w.ln_b[0].as<float>(), nullptr, Nq, C, q_f32, q_t,
+                                        (T*)nullptr, st)) return 2;
+            }
+            e->launches++;
         }
-        e->launches++;
         // ---- spatial cross-attention (spatial_cross_attention.py:128-175, :334-393)
         const int nq_sca = 8 * c.num_levels * c.sca_points * 3;
         if (gemm<T, float>(e, q_t, nullptr, 0, w.sca_q_w.as<float>(), w.sca_q_wh.p, w.sca_q_b.as<float>(), nullptr,
@@ -227,28 +246,40 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
                 return 2;
         }
         e->launches++;
-        if (gemm<T, float>(e, attn_out, nullptr, 0, w.sca_o_w.as<float>(), w.sca_o_wh.p, w.sca_o_b.as<float>(), q_f32,
-                           x_f32, Nq, C, C, ACT_NONE, st)) return 2;
-        if (e->taps)
-            OCC_CUDA(cudaMemcpyAsync(e->tap_sca.as<float>() + (size_t)l * Nq * C, x_f32, (size_t)Nq * C * 4,
-                                     cudaMemcpyDeviceToDevice, st));
-        {
-            ProfScope ps(e, st, CAT_LN);
-            if (launch_layernorm<T>(x_f32, w.ln_g[1].as<float>(), w.ln_b[1].as<float>(), nullptr, Nq, C, q_f32, q_t,
-                                    (T*)nullptr, st)) return 2;
+        if (fuse_ln) {
+            if (gemm_ln_fused(e, (const bf16*)attn_out, w.sca_o_wh.p, w.sca_o_b.as<float>(), q_f32, w.ln_g[1].as<float>(),
+                              w.ln_b[1].as<float>(), nullptr, x_f32, (bf16*)q_t, nullptr, Nq, C, st)) return 2;
+            std::swap(q_f32, x_f32);
+        } else {
+            if (gemm<T, float>(e, attn_out, nullptr, 0, w.sca_o_w.as<float>(), w.sca_o_wh.p, w.sca_o_b.as<float>(),
+                               q_f32, x_f32, Nq, C, C, ACT_NONE, st)) return 2;
+            if (e->taps)
+                OCC_CUDA(cudaMemcpyAsync(e->tap_sca.as<float>() + (size_t)l * Nq * C, x_f32, (size_t)Nq * C * 4,
+                                         cudaMemcpyDeviceToDevice, st));
+            {
+                ProfScope ps(e, st, CAT_LN);
+                if (launch_layernorm<T>(x_f32, w.ln_g[1].as<float>(), w.ln_b[1].as<float>(), nullptr, Nq, C, q_f32, q_t,
+                                        (T*)nullptr, st)) return 2;
+            }
+            e->launches++;
         }
-        e->launches++;
         // ---- FFN (mmcv FFN: x + W2 relu(W1 x))
         if (gemm<T, T>(e, q_t, nullptr, 0, w.ffn1_w.as<float>(), w.ffn1_wh.p, w.ffn1_b.as<float>(), nullptr,
                        e->ffn_h.as<T>(), Nq, c.ffn_dim, C, ACT_RELU, st)) return 2;
-        if (gemm<T, float>(e, e->ffn_h.as<T>(), nullptr, 0, w.ffn2_w.as<float>(), w.ffn2_wh.p, w.ffn2_b.as<float>(),
-                           q_f32, x_f32, Nq, C, c.ffn_dim, ACT_NONE, st)) return 2;
-        {
-            ProfScope ps(e, st, CAT_LN);
-            if (launch_layernorm<T>(x_f32, w.ln_g[2].as<float>(), w.ln_b[2].as<float>(), pos, Nq, C, q_f32, q_t, q_pos_t,
-                                    st)) return 2;
+        if (fuse_ln) {
+            if (gemm_ln_fused(e, e->ffn_h.as<bf16>(), w.ffn2_wh.p, w.ffn2_b.as<float>(), q_f32, w.ln_g[2].as<float>(),
+                              w.ln_b[2].as<float>(), pos, x_f32, (bf16*)q_t, (bf16*)q_pos_t, Nq, c.ffn_dim, st)) return 2;
+            std::swap(q_f32, x_f32);
+        } else {
+            if (gemm<T, float>(e, e->ffn_h.as<T>(), nullptr, 0, w.ffn2_w.as<float>(), w.ffn2_wh.p, w.ffn2_b.as<float>(),
+                               q_f32, x_f32, Nq, C, c.ffn_dim, ACT_NONE, st)) return 2;
+            {
+                ProfScope ps(e, st, CAT_LN);
+                if (launch_layernorm<T>(x_f32, w.ln_g[2].as<float>(), w.ln_b[2].as<float>(), pos, Nq, C, q_f32, q_t,
+                                        q_pos_t, st)) return 2;
+            }
+            e->launches++;
         }
-        e->launches++;
         if (e->taps)
             OCC_CUDA(cudaMemcpyAsync(e->tap_layer.as<float>() + (size_t)l * Nq * C, q_f32, (size_t)Nq * C * 4,
                                      cudaMemcpyDeviceToDevice, st));
@@ -262,21 +293,33 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
         ProfScope ps(e, st, CAT_VOX);
         if (launch_bev_to_voxel<T>(q_f32, c.bev_h, c.bev_w, Z, mid, e->vox0.as<T>(), st)) return 2;
     }
+    const bool conv_tc = sizeof(T) == 2 && c.use_tensor_cores && e->conv_wh[0].p && e->conv_wh[1].p && Z == 16;
     {
         ProfScope ps(e, st, CAT_CONV);
-        if (launch_conv3d_simt<T>(e->vox0.as<T>(), e->conv_w[0].as<float>(), e->conv_b[0].as<float>(), X, Y, Z, mid,
-                                  e->vox1.as<T>(), st)) return 2;
+        if (conv_tc) {
+            if (launch_conv3d_tc(e->vox0.as<bf16>(), e->conv_wh[0].as<bf16>(), e->conv_b[0].as<float>(), X, Y, Z, mid,
+                                 e->vox1.as<bf16>(), st)) return 2;
+        } else if (launch_conv3d_simt<T>(e->vox0.as<T>(), e->conv_w[0].as<float>(), e->conv_b[0].as<float>(), X, Y, Z,
+                                         mid, e->vox1.as<T>(), st)) return 2;
     }
     {
         ProfScope ps(e, st, CAT_CONV);
-        if (launch_conv3d_simt<T>(e->vox1.as<T>(), e->conv_w[1].as<float>(), e->conv_b[1].as<float>(), X, Y, Z,
-                                  c.out_dim, e->vox2.as<T>(), st)) return 2;
+        if (conv_tc) {
+            if (launch_conv3d_tc(e->vox1.as<bf16>(), e->conv_wh[1].as<bf16>(), e->conv_b[1].as<float>(), X, Y, Z,
+                                 c.out_dim, e->vox2.as<bf16>(), st)) return 2;
+        } else if (launch_conv3d_simt<T>(e->vox1.as<T>(), e->conv_w[1].as<float>(), e->conv_b[1].as<float>(), X, Y, Z,
+                                         c.out_dim, e->vox2.as<T>(), st)) return 2;
     }
     HeadWeights hw{e->hw1.as<float>(), e->hb1.as<float>(), e->hw2.as<float>(), e->hb2.as<float>(),
                    e->fw1.as<float>(), e->fb1.as<float>(), e->fw2.as<float>(), e->fb2.as<float>(), c.num_classes};
     {
         ProfScope ps(e, st, CAT_HEAD);
-        if (launch_occ_head<T>(e->vox2.as<T>(), hw, (int64_t)X * Y * Z, occ_logits, flow, cls_u8, cls_i64, st)) return 2;
+        if (conv_tc && e->head_w1h.p) {
+            if (launch_occ_head_tc(e->vox2.as<bf16>(), e->head_w1h.as<bf16>(), e->head_w2h.as<bf16>(),
+                                   e->head_b1c.as<float>(), e->head_b2c.as<float>(), c.num_classes, (int64_t)X * Y * Z,
+                                   occ_logits, flow, cls_u8, cls_i64, st)) return 2;
+        } else if (launch_occ_head<T>(e->vox2.as<T>(), hw, (int64_t)X * Y * Z, occ_logits, flow, cls_u8, cls_i64, st))
+            return 2;
     }
     e->launches += 4;
     return 0;
@@ -348,7 +391,7 @@ void occb200_engine_destroy(occb200_engine* e)
     }
     DevBuf* all[] = {&e->bev_queries, &e->pos, &e->cams_embeds, &e->level_embeds, &e->conv_w[0], &e->conv_w[1],
                      &e->conv_b[0], &e->conv_b[1], &e->conv_wh[0], &e->conv_wh[1], &e->hw1, &e->hb1, &e->hw2, &e->hb2,
-                     &e->fw1, &e->fb1, &e->fw2, &e->fb2, &e->head_wh, &e->tokens, &e->sca_value, &e->q_f32, &e->q_t,
+                     &e->fw1, &e->fb1, &e->fw2, &e->fb2, &e->head_w1h, &e->head_w2h, &e->head_b1c, &e->head_b2c, &e->tokens, &e->sca_value, &e->q_f32, &e->q_t,
                      &e->q_pos_t, &e->q0_t, &e->prev_t, &e->tsa_value, &e->tsa_value_prev, &e->qproj, &e->attn_out,
                      &e->x_f32, &e->ffn_h, &e->vox0, &e->vox1, &e->vox2, &e->hits, &e->tap_layer, &e->tap_tsa,
                      &e->tap_sca, &e->feats_dev[0], &e->feats_dev[1], &e->feats_dev[2], &e->feats_dev[3],
@@ -456,6 +499,14 @@ int occb200_engine_finalize(occb200_engine* e)
                     wf[((size_t)t * cin + ci) * od + co] = (*W)[((size_t)co * cin + ci) * 27 + t] * s;
         }
         if (upload(e->conv_w[i], wf.data(), wf.size()) || upload(e->conv_b[i], bf.data(), bf.size())) return 2;
+        if (tc) {                                             // tensor-core layout: [tap][cout][cin], K-major rows
+            std::vector<float> wt((size_t)27 * od * cin);
+            for (int t = 0; t < 27; ++t)
+                for (int co = 0; co < od; ++co)
+                    for (int ci = 0; ci < cin; ++ci)
+                        wt[((size_t)t * od + co) * cin + ci] = wf[((size_t)t * cin + ci) * od + co];
+            if (upload_bf16(e->conv_wh[i], wt.data(), wt.size())) return 2;
+        }
     }
     {
         GETP(w1, "transformer.predicter.0.weight", (size_t)2 * od * od);
@@ -470,6 +521,20 @@ int occb200_engine_finalize(occb200_engine* e)
             upload(e->hw2, w2->data(), w2->size()) || upload(e->hb2, b2->data(), b2->size()) ||
             upload(e->fw1, f1->data(), f1->size()) || upload(e->fb1, g1->data(), g1->size()) ||
             upload(e->fw2, f2->data(), f2->size()) || upload(e->fb2, g2->data(), g2->size())) return 2;
+        if (tc && od == 32 && c.num_classes + 2 <= 19) {          // tensor-core head: concatenated / block-diagonal weights
+            const int H = 2 * od, nc = c.num_classes;
+            std::vector<float> w1c((size_t)2 * H * od), b1c(2 * H), w2c((size_t)32 * 2 * H, 0.f), b2c(nc + 2);
+            for (int i = 0; i < H * od; ++i) { w1c[i] = (*w1)[i]; w1c[(size_t)H * od + i] = (*f1)[i]; }
+            for (int i = 0; i < H; ++i) { b1c[i] = (*b1)[i]; b1c[H + i] = (*g1)[i]; }
+            for (int r = 0; r < nc; ++r)
+                for (int k = 0; k < H; ++k) w2c[(size_t)r * 2 * H + k] = (*w2)[(size_t)r * H + k];
+            for (int r = 0; r < 2; ++r)
+                for (int k = 0; k < H; ++k) w2c[(size_t)(nc + r) * 2 * H + H + k] = (*f2)[(size_t)r * H + k];
+            for (int i = 0; i < nc; ++i) b2c[i] = (*b2)[i];
+            b2c[nc] = (*g2)[0]; b2c[nc + 1] = (*g2)[1];
+            if (upload_bf16(e->head_w1h, w1c.data(), w1c.size()) || upload_bf16(e->head_w2h, w2c.data(), w2c.size()) ||
+                upload(e->head_b1c, b1c.data(), b1c.size()) || upload(e->head_b2c, b2c.data(), b2c.size())) return 2;
+        }
     }
     // workspace
     const size_t es = e->elt();

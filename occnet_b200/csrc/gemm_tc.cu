@@ -7,13 +7,16 @@
 //   warp 0   TMA producer : A tile 128x64 + W tile BNx64 (bf16, 128B swizzle) per k-block, 4-stage mbarrier ring
 //   warp 1   MMA issuer   : tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16 x4 per stage;
 //                           accumulators double-buffered in TMEM (2 x 256 columns)
-//   warps 2-5 epilogue    : tcgen05.ld 32x32b -> bias / ReLU / residual -> global store (fp32 or bf16),
-//                           overlapping the next tile's main loop
+//   warps 2-9 epilogue    : tcgen05.ld 32x32b -> bias / ReLU / residual -> global store (fp32 or bf16), or the fused
+//                           LayerNorm (x written back to TMEM with tcgen05.st, row statistics, second pass);
+//                           overlaps the next tile's main loop.  Weights stay resident in shared memory when they fit.
 // The A operand may be the concatenation of two matrices along K (TSA's cat([value, query+pos]),
 // temporal_self_attention.py:197) -- two tensor maps, no materialised concat.
-#include <mutex>
+#include <cstdlib>
 #include <map>
+#include <mutex>
 #include <tuple>
+#include <vector>
 
 #include "gemm_tc.cuh"
 #include "tc_common.cuh"
@@ -56,33 +59,60 @@ int make_tensor_map_bf16(CUtensorMap* map, const void* base, int rank, const uin
 
 namespace {
 
-constexpr int BLOCK_M = 128, BLOCK_K = 64, STAGES = 4, A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int NUM_THREADS = 192;
+constexpr int BLOCK_M = 128, BLOCK_K = 64, A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int NUM_THREADS = 320;                          // TMA warp, MMA warp, 8 epilogue warps
+constexpr int SMEM_TAIL = 256 + 2048 + 8 * 4096;          // barriers, LN partials, 8 staging blocks
+constexpr int SMEM_LIMIT = 232448 - 1024 - SMEM_TAIL;          // 227 KB opt-in maximum minus alignment slack and barriers
+constexpr int MAX_STAGES = 6;
 
-template <typename TC>
+struct LnArgs {                                           // fused LayerNorm epilogue (N == BN == 256)
+    const float* gamma; const float* beta; const float* pos;
+    float* y_f32; bf16* y_bf16; bf16* y_pos_bf16;
+};
+
+// w_resident: all nk weight k-blocks of this CTA's n-block stay in shared memory for the CTA's lifetime and the
+// ring only carries A tiles; otherwise each stage carries an A tile and a W k-block (v1 behaviour).
+template <typename TC, bool LN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmW, const float* __restrict__ bias,
-               const float* __restrict__ residual, TC* __restrict__ C, int M, int N, int BN, int nk, int nk1, int act)
+               const float* __restrict__ residual, TC* __restrict__ C, LnArgs ln, int M, int N, int BN, int nk,
+               int nk1, int act, int w_resident, int stages, long long* __restrict__ dbg)
 {
+    // optional in-kernel timeline (globaltimer ns): 16 slots per CTA, written by the role that owns the event
+    auto stamp = [&](int slot) {
+        if (dbg) {
+            long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            dbg[(size_t)blockIdx.x * 16 + slot] = t;
+        }
+    };
+    if (threadIdx.x == 0) stamp(0);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t stage_bytes = A_TILE_BYTES + BN * BLOCK_K * 2;
-    const uint32_t bar_base = smem_base + STAGES * stage_bytes;
+    const uint32_t w_tile_bytes = BN * BLOCK_K * 2;
+    const uint32_t w_region = w_resident ? nk * w_tile_bytes : 0;
+    const uint32_t stage_bytes = A_TILE_BYTES + (w_resident ? 0 : w_tile_bytes);
+    const uint32_t ring_base = smem_base + w_region;
+    const uint32_t bar_base = ring_base + stages * stage_bytes;
     auto full_bar = [&](int s) { return bar_base + s * 8; };
-    auto empty_bar = [&](int s) { return bar_base + (STAGES + s) * 8; };
-    auto tfull_bar = [&](int s) { return bar_base + (2 * STAGES + s) * 8; };
-    auto tempty_bar = [&](int s) { return bar_base + (2 * STAGES + 2 + s) * 8; };
-    const uint32_t tmem_slot = bar_base + (2 * STAGES + 4) * 8;
+    auto empty_bar = [&](int s) { return bar_base + (MAX_STAGES + s) * 8; };
+    auto tfull_bar = [&](int s) { return bar_base + (2 * MAX_STAGES + s) * 8; };
+    auto tempty_bar = [&](int s) { return bar_base + (2 * MAX_STAGES + 2 + s) * 8; };
+    const uint32_t w_bar = bar_base + (2 * MAX_STAGES + 4) * 8;
+    const uint32_t tmem_slot = bar_base + (2 * MAX_STAGES + 5) * 8;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = N / BN;
-    const int num_tiles = m_tiles * n_tiles;
+    // CTA -> (fixed n block, strided m tiles) so that a resident weight block serves every tile of the CTA
+    const int n_blk = blockIdx.x % n_tiles;
+    const int m_first = blockIdx.x / n_tiles, m_step = gridDim.x / n_tiles;
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmA); tc::tma_prefetch_desc(&tmA2); tc::tma_prefetch_desc(&tmW);
-        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(full_bar(s), 1); tc::mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; ++s) { tc::mbar_init(tfull_bar(s), 1); tc::mbar_init(tempty_bar(s), 128); }
+        for (int s = 0; s < stages; ++s) { tc::mbar_init(full_bar(s), 1); tc::mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(tfull_bar(s), 1); tc::mbar_init(tempty_bar(s), 256); }
+        tc::mbar_init(w_bar, 1);
         tc::mbar_fence_init();
     }
     if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
@@ -91,123 +121,260 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc::tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    if (threadIdx.x == 0) stamp(1);                              // setup done (barriers, TMEM)
 
     if (warp == 0) {
         if (lane == 0) {
+            if (w_resident) {
+                tc::mbar_arrive_expect_tx(w_bar, w_region);
+                for (int kb = 0; kb < nk; ++kb)
+                    tc::tma_load_2d(smem_base + kb * w_tile_bytes, &tmW, w_bar, kb * BLOCK_K, n_blk * BN);
+            }
             int s = 0; uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            for (int m_blk = m_first; m_blk < m_tiles; m_blk += m_step) {
                 for (int kb = 0; kb < nk; ++kb) {
                     tc::mbar_wait(empty_bar(s), ph ^ 1);
                     tc::mbar_arrive_expect_tx(full_bar(s), stage_bytes);
-                    const uint32_t a_dst = smem_base + s * stage_bytes;
+                    const uint32_t a_dst = ring_base + s * stage_bytes;
                     if (kb < nk1) tc::tma_load_2d(a_dst, &tmA, full_bar(s), kb * BLOCK_K, m_blk * BLOCK_M);
                     else          tc::tma_load_2d(a_dst, &tmA2, full_bar(s), (kb - nk1) * BLOCK_K, m_blk * BLOCK_M);
-                    tc::tma_load_2d(a_dst + A_TILE_BYTES, &tmW, full_bar(s), kb * BLOCK_K, n_blk * BN);
-                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                    if (!w_resident)
+                        tc::tma_load_2d(a_dst + A_TILE_BYTES, &tmW, full_bar(s), kb * BLOCK_K, n_blk * BN);
+                    if (++s == stages) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        const uint32_t idesc = tc::make_idesc_bf16(BLOCK_M, BN);
-        int s = 0; uint32_t ph = 0; int as = 0; uint32_t aph = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            if (lane == 0) {
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc_bf16(BLOCK_M, BN);
+            int s = 0; uint32_t ph = 0; int as = 0; uint32_t aph = 0;
+            if (w_resident) { tc::mbar_wait(w_bar, 0); tc::tc_fence_after(); }
+            stamp(2);                                            // weights resident
+            int tcount = 0;
+            for (int m_blk = m_first; m_blk < m_tiles; m_blk += m_step, ++tcount) {
                 tc::mbar_wait(tempty_bar(as), aph ^ 1);
                 tc::tc_fence_after();
-            }
-            __syncwarp();
-            for (int kb = 0; kb < nk; ++kb) {
-                if (lane == 0) {
+                for (int kb = 0; kb < nk; ++kb) {
                     tc::mbar_wait(full_bar(s), ph);
+                    if (kb == 0 && tcount < 3) stamp(3 + tcount * 3);    // first A k-block of tile landed
                     tc::tc_fence_after();
-                    const uint32_t a_addr = smem_base + s * stage_bytes;
+                    const uint32_t a_addr = ring_base + s * stage_bytes;
                     const uint64_t da = tc::make_smem_desc(a_addr, 128);
-                    const uint64_t db = tc::make_smem_desc(a_addr + A_TILE_BYTES, 128);
+                    const uint64_t db = tc::make_smem_desc(w_resident ? smem_base + kb * w_tile_bytes
+                                                                      : a_addr + A_TILE_BYTES, 128);
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / 16; ++k)      // +32 bytes (>>4 = 2) per UMMA_K step inside the swizzle atom
+                    for (int k = 0; k < BLOCK_K / 16; ++k)       // +32 bytes (>>4 = 2) per UMMA_K step inside the swizzle atom
                         tc::umma_bf16(tmem_base + as * 256, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
                     tc::umma_commit(empty_bar(s));               // frees the smem stage when these MMAs retire
                     if (kb == nk - 1) tc::umma_commit(tfull_bar(as));
+                    if (++s == stages) { s = 0; ph ^= 1; }
                 }
-                __syncwarp();
-                if (++s == STAGES) { s = 0; ph ^= 1; }
+                if (++as == 2) { as = 0; aph ^= 1; }
             }
-            if (++as == 2) { as = 0; aph ^= 1; }
         }
     } else {
-        const int quarter = warp & 3;                            // TMEM lane quarter this warp may access
+        // 8 epilogue warps: warp -> (TMEM lane quarter = warp % 4, column half).  tcgen05.ld hands every thread one
+        // ROW of the tile; touching global memory in that shape costs 32 separate requests per instruction and is
+        // request-rate bound (measured: ~7 us per tile).  So every global access goes through a per-warp 4 KB
+        // staging block in shared memory (128-byte rows, 16-byte pieces XOR-swizzled by row) and is issued in the
+        // transposed shape: one instruction = 4 rows x 128 contiguous bytes.
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int ew = warp - 2;
+        const int ncol = BN >> 1;                                // columns owned by this warp
+        const int cbeg = half * ncol;
+        const uint32_t stg = bar_base + 256 + 2048 + ew * 4096;  // this warp's staging block (shared address)
+        float2* part = reinterpret_cast<float2*>(smem_raw + (bar_base + 256 - tc::smem_u32(smem_raw)));   // [2][128]
+        const int crow = lane >> 3, cpiece = lane & 7;           // coalesced shape: row 4*i + crow, 16-byte piece cpiece
+        auto sts4 = [&](int r, int piece, float4 v) {
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + r * 128 + ((piece ^ (r & 7)) << 4)),
+                         "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+        };
+        auto lds4 = [&](int r, int piece) {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                         : "r"(stg + r * 128 + ((piece ^ (r & 7)) << 4)) : "memory");
+            return v;
+        };
         int as = 0; uint32_t aph = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-            tc::mbar_wait(tfull_bar(as), aph);
-            tc::tc_fence_after();
-            const int row = m_blk * BLOCK_M + quarter * 32 + lane;
+        int etile = 0;
+        for (int m_blk = m_first; m_blk < m_tiles; m_blk += m_step) {
+            const int row0 = m_blk * BLOCK_M + quarter * 32;     // first row of this warp's 32-row block
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * 256;
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t r[32];
-                tc::tmem_ld32(taddr + c0, r);
-                tc::tmem_ld_wait();
-                if (row < M) {
+            // coalesced fetch of a [32 rows x 32 cols] fp32 block (rows row0.., columns c..c+31) into registers
+            float4 pre[8];
+            auto fetch = [&](const float* base, int ld, int c) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = row0 + 4 * i + crow;
+                    pre[i] = (base != nullptr && r < M) ? __ldg(reinterpret_cast<const float4*>(base + (size_t)r * ld + c) + cpiece)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            // registers (coalesced shape) -> staging -> this thread's row (v[32])
+            auto to_rows = [&](float (&v)[32]) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sts4(4 * i + crow, cpiece, pre[i]);
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 t = lds4(lane, j);
+                    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+                }
+                __syncwarp();
+            };
+            fetch(residual, N, n_blk * BN + cbeg);               // independent of the MMA: issue before waiting on it
+            tc::mbar_wait(tfull_bar(as), aph);
+            if (warp == 2 && lane == 0 && etile < 3) stamp(4 + etile * 3);          // accumulator ready
+            tc::tc_fence_after();
+            if constexpr (LN) {
+                float sum = 0.f, sumsq = 0.f;
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci) {                 // 128 columns = 4 chunks per warp
+                    const int c0 = cbeg + ci * 32;
+                    float q[32];
+                    to_rows(q);                                  // residual of my row, this chunk
+                    if (ci + 1 < 4) fetch(residual, 256, c0 + 32);
+                    uint32_t r[32];
+                    tc::tmem_ld32(taddr + c0, r);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0) + i);
+                        const float x0 = __uint_as_float(r[4 * i]) + b.x + q[4 * i], x1 = __uint_as_float(r[4 * i + 1]) + b.y + q[4 * i + 1];
+                        const float x2 = __uint_as_float(r[4 * i + 2]) + b.z + q[4 * i + 2], x3 = __uint_as_float(r[4 * i + 3]) + b.w + q[4 * i + 3];
+                        sum += (x0 + x1) + (x2 + x3);
+                        sumsq = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, fmaf(x3, x3, sumsq))));
+                        r[4 * i] = __float_as_uint(x0); r[4 * i + 1] = __float_as_uint(x1);
+                        r[4 * i + 2] = __float_as_uint(x2); r[4 * i + 3] = __float_as_uint(x3);
+                    }
+                    tc::tmem_st32(taddr + c0, r);
+                }
+                if (ln.y_pos_bf16) fetch(ln.pos, 256, cbeg);
+                // exchange the half-row statistics with the warp that owns the other 128 columns of these rows
+                part[half * 128 + quarter * 32 + lane] = make_float2(sum, sumsq);
+                tc::tmem_st_wait();
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+                const float2 other = part[(half ^ 1) * 128 + quarter * 32 + lane];
+                const float mean = (sum + other.x) * (1.f / 256.f);
+                const float var = fmaxf((sumsq + other.y) * (1.f / 256.f) - mean * mean, 0.f);
+                const float rstd = rsqrtf(var + 1e-5f);
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci) {
+                    const int c0 = cbeg + ci * 32;
+                    uint32_t r[32];
+                    tc::tmem_ld32(taddr + c0, r);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {                // normalise my row, stage it
+                        const float4 g = __ldg(reinterpret_cast<const float4*>(ln.gamma + c0) + j);
+                        const float4 be = __ldg(reinterpret_cast<const float4*>(ln.beta + c0) + j);
+                        float4 y;
+                        y.x = (__uint_as_float(r[4 * j]) - mean) * rstd * g.x + be.x;
+                        y.y = (__uint_as_float(r[4 * j + 1]) - mean) * rstd * g.y + be.y;
+                        y.z = (__uint_as_float(r[4 * j + 2]) - mean) * rstd * g.z + be.z;
+                        y.w = (__uint_as_float(r[4 * j + 3]) - mean) * rstd * g.w + be.w;
+                        sts4(lane, j, y);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {                // coalesced stores: 4 rows x 128 B per instruction
+                        const int rr = 4 * i + crow, grow = row0 + rr;
+                        const float4 y = lds4(rr, cpiece);
+                        if (grow < M) {
+                            const size_t o = (size_t)grow * 256 + c0 + cpiece * 4;
+                            if (ln.y_f32) *reinterpret_cast<float4*>(ln.y_f32 + o) = y;
+                            if (ln.y_bf16)
+                                *reinterpret_cast<uint2*>(ln.y_bf16 + o) = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+                            if (ln.y_pos_bf16) {
+                                const float4 p4 = pre[i];
+                                *reinterpret_cast<uint2*>(ln.y_pos_bf16 + o) =
+                                    make_uint2(pack_bf16x2(y.x + p4.x, y.y + p4.y), pack_bf16x2(y.z + p4.z, y.w + p4.w));
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (ln.y_pos_bf16 && ci + 1 < 4) fetch(ln.pos, 256, c0 + 32);
+                }
+            } else {
+                const int nchunk = ncol >> 5;                    // BN/2 is a multiple of 32 for every plan (<= 4 chunks)
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci) {
+                    if (ci >= nchunk) break;
+                    const int c0 = cbeg + ci * 32;
                     const int col = n_blk * BN + c0;
-                    float v[32];
+                    uint32_t r[32];
+                    tc::tmem_ld32(taddr + c0, r);
+                    tc::tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                    if (bias) {
+                    for (int j = 0; j < 8; ++j)                  // stage my row of the accumulator
+                        sts4(lane, j, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                  __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+                    __syncwarp();
+                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + col) + cpiece);
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col + i));
-                            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                    for (int i = 0; i < 8; ++i) {                // bias / act / residual / store in the coalesced shape
+                        const int rr = 4 * i + crow, grow = row0 + rr;
+                        float4 v = lds4(rr, cpiece);
+                        v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+                        if (act == ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                        if (residual) { const float4 q = pre[i]; v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
+                        if (grow < M) {
+                            const size_t o = (size_t)grow * N + col + cpiece * 4;
+                            if constexpr (sizeof(TC) == 4) *reinterpret_cast<float4*>(reinterpret_cast<float*>(C) + o) = v;
+                            else *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(C) + o) =
+                                     make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
                         }
                     }
-                    if (act == ACT_RELU) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-                    }
-                    if (residual) {
-                        const float4* rp = reinterpret_cast<const float4*>(residual + (size_t)row * N + col);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 b = __ldg(rp + i);
-                            v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-                        }
-                    }
-                    if constexpr (sizeof(TC) == 4) {
-                        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(C) + (size_t)row * N + col);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                    } else {
-                        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(C) + (size_t)row * N + col);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            uint4 u;
-                            u.x = pack_bf16x2(v[8 * i], v[8 * i + 1]); u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-                            u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-                            op[i] = u;
-                        }
-                    }
+                    __syncwarp();
+                    if (residual && ci + 1 < nchunk) fetch(residual, N, col + 32);
                 }
             }
             tc::tc_fence_before();
             tc::mbar_arrive(tempty_bar(as));
+            if (warp == 2 && lane == 0 && etile < 3) stamp(5 + etile * 3);          // epilogue of tile done
+            ++etile;
             if (++as == 2) { as = 0; aph ^= 1; }
         }
     }
     tc::tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) stamp(15);
     if (warp == 1) {
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, 512);
     }
 }
 
-int pick_bn(int N)
+// tile-N choice: prefer a weight block that fits resident (<= 128 KB) next to >= 4 A stages
+struct Plan { int BN, resident, stages, smem; };
+
+Plan make_plan(int N, int K, bool ln)
 {
-    if (N <= 256) return N;
-    if (N % 256 == 0) return 256;
-    if (N % 192 == 0) return 192;
-    if (N % 128 == 0) return 128;
-    return 0;
+    Plan p{0, 0, 0, 0};
+    const int cands[] = {256, 192, 128, 64};                  // BN/2 must be a multiple of 32 (epilogue column split)
+    if (ln) {
+        p.BN = 256;
+    } else {
+        for (int bn : cands) {
+            if (N % bn != 0 || bn > N) continue;
+            if ((long)bn * K * 2 <= 131072) { p.BN = bn; break; }
+        }
+        if (p.BN == 0) {                                      // no resident candidate: largest tile that divides N
+            for (int bn : cands) if (N % bn == 0 && bn <= N) { p.BN = bn; break; }
+        }
+        if (p.BN == 0 && N <= 256 && N % 64 == 0) p.BN = N;
+    }
+    if (p.BN == 0) return p;
+    const int w_bytes = p.BN * K * 2;
+    p.resident = w_bytes <= 131072;
+    const int stage = A_TILE_BYTES + (p.resident ? 0 : p.BN * BLOCK_K * 2);
+    const int avail = SMEM_LIMIT - (p.resident ? w_bytes : 0);
+    p.stages = avail / stage;
+    if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+    p.smem = 1024 + (p.resident ? w_bytes : 0) + p.stages * stage + SMEM_TAIL;
+    return p;
 }
 
 struct MapKey {
@@ -234,41 +401,84 @@ int cached_map_2d(const void* base, uint64_t inner, uint64_t rows, uint32_t box_
     return 0;
 }
 
-}  // namespace
-
-bool gemm_tc_supported(int M, int N, int K, int K1)
-{
-    const int bn = pick_bn(N);
-    return M > 0 && bn >= 16 && bn % 16 == 0 && K % 64 == 0 && K1 % 64 == 0 && K1 > 0 && K1 <= K;
-}
-
-template <typename TC>
-int gemm_tc(const bf16* A, const bf16* A2, int K1, const bf16* W, const float* bias, const float* residual, TC* C,
-            int M, int N, int K, int act, cudaStream_t stream)
+template <typename TC, bool LN>
+int launch(const bf16* A, const bf16* A2, int K1, const bf16* W, const float* bias, const float* residual, TC* C,
+           LnArgs ln, int M, int N, int K, int act, cudaStream_t stream)
 {
     if (A2 == nullptr) K1 = K;
-    OCC_CHECK(gemm_tc_supported(M, N, K, K1), "gemm_tc: unsupported shape");
-    const int BN = pick_bn(N);
+    const Plan p = make_plan(N, K, LN);
+    OCC_CHECK(p.BN > 0 && p.stages >= 2 && K % 64 == 0 && K1 % 64 == 0 && M > 0, "gemm_tc: unsupported shape");
     CUtensorMap tmA, tmA2, tmW;
     if (cached_map_2d(A, (uint64_t)K1, (uint64_t)M, BLOCK_K, BLOCK_M, &tmA)) return 1;
     if (A2) { if (cached_map_2d(A2, (uint64_t)(K - K1), (uint64_t)M, BLOCK_K, BLOCK_M, &tmA2)) return 1; }
     else tmA2 = tmA;
-    if (cached_map_2d(W, (uint64_t)K, (uint64_t)N, BLOCK_K, (uint32_t)BN, &tmW)) return 1;
-    const int stage_bytes = A_TILE_BYTES + BN * BLOCK_K * 2;
-    const int smem = 1024 + STAGES * stage_bytes + 256;
+    if (cached_map_2d(W, (uint64_t)K, (uint64_t)N, BLOCK_K, (uint32_t)p.BN, &tmW)) return 1;
     static int num_sms = 0;
     if (num_sms == 0) {
         int dev = 0;
         OCC_CUDA(cudaGetDevice(&dev));
         OCC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    OCC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M, tiles = m_tiles * (N / BN);
-    const int grid = tiles < num_sms ? tiles : num_sms;
-    gemm_tc_kernel<TC><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmA2, tmW, bias, residual, C, M, N, BN, K / BLOCK_K,
-                                                           K1 / BLOCK_K, act);
+    static bool attr_set = false;
+    if (!attr_set) {
+        OCC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<TC, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        attr_set = true;
+    }
+    const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = N / p.BN;
+    int per_n = num_sms / n_tiles;
+    if (per_n > m_tiles) per_n = m_tiles;
+    const int grid = per_n * n_tiles;
+    long long* dbg = nullptr;
+    static const bool want_dbg = getenv("OCC_GEMM_TIMELINE") != nullptr;
+    if (want_dbg) {
+        OCC_CUDA(cudaMalloc(&dbg, (size_t)grid * 16 * sizeof(long long)));
+        OCC_CUDA(cudaMemsetAsync(dbg, 0, (size_t)grid * 16 * sizeof(long long), stream));
+    }
+    gemm_tc_kernel<TC, LN><<<grid, NUM_THREADS, p.smem, stream>>>(tmA, tmA2, tmW, bias, residual, C, ln, M, N, p.BN,
+                                                                 K / BLOCK_K, K1 / BLOCK_K, act, p.resident, p.stages, dbg);
     OCC_CUDA(cudaGetLastError());
+    if (want_dbg) {                                               // development aid: per-CTA timeline in ns
+        std::vector<long long> h((size_t)grid * 16);
+        OCC_CUDA(cudaStreamSynchronize(stream));
+        OCC_CUDA(cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(dbg);
+        long long t0 = h[0];
+        for (int b = 0; b < grid; ++b) if (h[(size_t)b * 16] && h[(size_t)b * 16] < t0) t0 = h[(size_t)b * 16];
+        fprintf(stderr, "[gemm timeline] M=%d N=%d K=%d BN=%d resident=%d stages=%d grid=%d LN=%d\n", M, N, K, p.BN,
+                p.resident, p.stages, grid, (int)LN);
+        const int show[] = {0, 1, grid / 2, grid - 1};
+        for (int b : show) {
+            fprintf(stderr, "  cta %3d:", b);
+            for (int i = 0; i < 16; ++i) fprintf(stderr, " %6lld", h[(size_t)b * 16 + i] ? h[(size_t)b * 16 + i] - t0 : -1);
+            fprintf(stderr, "\n");
+        }
+    }
     return 0;
+}
+
+}  // namespace
+
+bool gemm_tc_supported(int M, int N, int K, int K1)
+{
+    const Plan p = make_plan(N, K, false);
+    return M > 0 && p.BN >= 64 && p.BN % 64 == 0 && p.stages >= 2 && K % 64 == 0 && K1 % 64 == 0 && K1 > 0 && K1 <= K;
+}
+
+template <typename TC>
+int gemm_tc(const bf16* A, const bf16* A2, int K1, const bf16* W, const float* bias, const float* residual, TC* C,
+            int M, int N, int K, int act, cudaStream_t stream)
+{
+    return launch<TC, false>(A, A2, K1, W, bias, residual, C, LnArgs{}, M, N, K, act, stream);
+}
+
+int gemm_tc_ln(const bf16* A, const bf16* W, const float* bias, const float* residual, const float* gamma,
+               const float* beta, const float* pos, float* y_f32, bf16* y_bf16, bf16* y_pos_bf16, int M, int K,
+               cudaStream_t stream)
+{
+    OCC_CHECK(bias && residual && gamma && beta, "gemm_tc_ln: bias, residual, gamma, beta are required");
+    OCC_CHECK(y_pos_bf16 == nullptr || pos != nullptr, "gemm_tc_ln: pos required for y_pos");
+    return launch<float, true>(A, nullptr, 0, W, bias, residual, (float*)nullptr, LnArgs{gamma, beta, pos, y_f32, y_bf16, y_pos_bf16},
+                               M, 256, K, ACT_NONE, stream);
 }
 
 template int gemm_tc<float>(const bf16*, const bf16*, int, const bf16*, const float*, const float*, float*, int, int,

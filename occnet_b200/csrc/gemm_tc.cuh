@@ -11,6 +11,12 @@ template <typename TC>
 int gemm_tc(const bf16* A, const bf16* A2, int K1, const bf16* W, const float* bias, const float* residual, TC* C,
             int M, int N, int K, int act, cudaStream_t stream);
 
+// Same GEMM with N = 256 and a fused epilogue  y = LayerNorm(A.W^T + bias + residual) (eps 1e-5):
+// writes the fp32 residual stream, the bf16 operand copy and (optionally) the bf16 copy of y + pos.
+int gemm_tc_ln(const bf16* A, const bf16* W, const float* bias, const float* residual, const float* gamma,
+               const float* beta, const float* pos, float* y_f32, bf16* y_bf16, bf16* y_pos_bf16, int M, int K,
+               cudaStream_t stream);
+
 int launch_bf16_to_f32(const bf16* src, float* dst, int64_t n, cudaStream_t stream);
 
 }  // namespace occ

@@ -53,6 +53,58 @@ __device__ __forceinline__ void bilinear_acc8(const T* __restrict__ base, int H,
     }
 }
 
+// ---- fused-kernel sample pipeline: the owner lane of a (head, level) turns one sampling location into a
+// packed descriptor (clamped pixel offset + which neighbours exist) and four pre-multiplied corner weights;
+// the four lanes of the head then gather their 8 channels with unconditional, in-bounds 128-bit loads.
+struct SamplePrep { int code; float c1, c2, c3, c4; };
+constexpr int CODE_DW = 1 << 20, CODE_DH = 1 << 21, CODE_VALID = 1 << 22, CODE_OFF_MASK = (1 << 20) - 1;
+
+__device__ __forceinline__ SamplePrep prep_sample(float h_im, float w_im, float wt, int H, int W)
+{
+    SamplePrep s;
+    const bool valid = h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W;   // mmcv kernel's test
+    const float hf = valid ? floorf(h_im) : 0.f, wf = valid ? floorf(w_im) : 0.f;
+    const int h_lo = (int)hf, w_lo = (int)wf;
+    const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
+    const bool top = h_lo >= 0, bot = h_lo + 1 <= H - 1, lef = w_lo >= 0, rig = w_lo + 1 <= W - 1;
+    s.c1 = (valid && top && lef) ? wt * (hh * hw) : 0.f;
+    s.c2 = (valid && top && rig) ? wt * (hh * lw) : 0.f;
+    s.c3 = (valid && bot && lef) ? wt * (lh * hw) : 0.f;
+    s.c4 = (valid && bot && rig) ? wt * (lh * lw) : 0.f;
+    const int h0 = max(h_lo, 0), h1 = min(h_lo + 1, H - 1), w0 = max(w_lo, 0), w1 = min(w_lo + 1, W - 1);
+    s.code = (h0 * W + w0) | ((w1 - w0) ? CODE_DW : 0) | ((h1 - h0) ? CODE_DH : 0) | (valid ? CODE_VALID : 0);
+    return s;
+}
+
+// acc(2 lanes) += a * w using the packed fp32x2 FMA of sm_100
+__device__ __forceinline__ void ffma2(float2& acc, float a0, float a1, float w)
+{
+    unsigned long long d = *reinterpret_cast<unsigned long long*>(&acc);
+    const float2 av = make_float2(a0, a1), wv = make_float2(w, w);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;"
+        : "+l"(d)
+        : "l"(*reinterpret_cast<const unsigned long long*>(&av)), "l"(*reinterpret_cast<const unsigned long long*>(&wv)));
+    acc = *reinterpret_cast<float2*>(&d);
+}
+
+template <typename T>
+__device__ __forceinline__ void gather_sample(const T* __restrict__ base, int W, int code, float c1, float c2, float c3,
+                                              float c4, float2 (&acc)[4])
+{
+    if (!(code & CODE_VALID)) return;                            // uniform inside the 4-lane head group
+    const T* p = base + (int64_t)(code & CODE_OFF_MASK) * 256;
+    const int dw = (code & CODE_DW) ? 256 : 0, dh = (code & CODE_DH) ? W * 256 : 0;
+    float v1[8], v2[8], v3[8], v4[8];
+    load8(p, v1); load8(p + dw, v2); load8(p + dh, v3); load8(p + dh + dw, v4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        ffma2(acc[i], v1[2 * i], v1[2 * i + 1], c1);
+        ffma2(acc[i], v2[2 * i], v2[2 * i + 1], c2);
+        ffma2(acc[i], v3[2 * i], v3[2 * i + 1], c3);
+        ffma2(acc[i], v4[2 * i], v4[2 * i + 1], c4);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Operator boundary: value [B,Nv,M,C] f32, loc [B,Nq,M,L,P,2] (x,y), w [B,Nq,M,L,P] -> [B,Nq,M*C]
 // One thread per (b, q, head, 8-channel slice) when C % 8 == 0, otherwise per channel.
@@ -140,22 +192,32 @@ tsa_fused_kernel(const T* __restrict__ value_prev, const T* __restrict__ value_c
     const float wim1 = __fadd_rn(rx, __fdiv_rn(off.z, fw)) * fw - 0.5f;
     const float him1 = __fadd_rn(ry, __fdiv_rn(off.w, fh)) * fh - 0.5f;
 
-    float acc[8];
+    const SamplePrep sa = prep_sample(him0, wim0, wt0, bev_h, bev_w);
+    const SamplePrep sb = prep_sample(him1, wim1, wt1, bev_h, bev_w);
+    float2 acc2[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 4; ++i) acc2[i] = make_float2(0.f, 0.f);
     const int grp = lane & ~3;
 #pragma unroll
     for (int o = 0; o < 4; ++o) {                            // owner sub-lane o holds samples (o>>1, (o&1)*2 + {0,1})
         const int src = grp | o;
-        const float a_w = __shfl_sync(0xffffffffu, wim0, src), a_h = __shfl_sync(0xffffffffu, him0, src);
-        const float b_w = __shfl_sync(0xffffffffu, wim1, src), b_h = __shfl_sync(0xffffffffu, him1, src);
-        const float a_t = __shfl_sync(0xffffffffu, wt0, src), b_t = __shfl_sync(0xffffffffu, wt1, src);
         const T* base = ((o >> 1) == 0 ? value_prev : value_cur) + head * 32 + s * 8;
-        bilinear_acc8<T>(base, bev_h, bev_w, 256, a_h, a_w, a_t, acc);
-        bilinear_acc8<T>(base, bev_h, bev_w, 256, b_h, b_w, b_t, acc);
+        {
+            const int code = __shfl_sync(0xffffffffu, sa.code, src);
+            const float c1 = __shfl_sync(0xffffffffu, sa.c1, src), c2 = __shfl_sync(0xffffffffu, sa.c2, src);
+            const float c3 = __shfl_sync(0xffffffffu, sa.c3, src), c4 = __shfl_sync(0xffffffffu, sa.c4, src);
+            gather_sample<T>(base, bev_w, code, c1, c2, c3, c4, acc2);
+        }
+        {
+            const int code = __shfl_sync(0xffffffffu, sb.code, src);
+            const float c1 = __shfl_sync(0xffffffffu, sb.c1, src), c2 = __shfl_sync(0xffffffffu, sb.c2, src);
+            const float c3 = __shfl_sync(0xffffffffu, sb.c3, src), c4 = __shfl_sync(0xffffffffu, sb.c4, src);
+            gather_sample<T>(base, bev_w, code, c1, c2, c3, c4, acc2);
+        }
     }
+    float acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] *= 0.5f;
+    for (int i = 0; i < 4; ++i) { acc[2 * i] = acc2[i].x * 0.5f; acc[2 * i + 1] = acc2[i].y * 0.5f; }
     store8(out + (int64_t)q * 256 + head * 32 + s * 8, acc);
 }
 
@@ -199,7 +261,7 @@ __global__ void project_pillars_kernel(ScaParams sp, float* __restrict__ ref_cam
 //   out  [Nq, 256] T  = sum_{visible cams} MSDA_cam(q) / max(1, #visible cams)
 //   hits (optional) [Nq] u8 = #visible cams (for tests / statistics)
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 sca_fused_kernel(const T* __restrict__ value, const float* __restrict__ qproj, ScaParams sp, LevelGeom lg,
                  int Nv, T* __restrict__ out, uint8_t* __restrict__ hits)
 {
@@ -227,17 +289,20 @@ sca_fused_kernel(const T* __restrict__ value, const float* __restrict__ qproj, S
     const int count = __popc(vis);
     if (hits && lane == 0) hits[q] = (uint8_t)count;
 
-    float acc[8];
+    float2 acc2[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 4; ++i) acc2[i] = make_float2(0.f, 0.f);
 
     if (count > 0) {
         // ---- owner lane (head, level = s): 8 points x (dx, dy) and 8 logits
+        // (static selects instead of lg.w[s]: a dynamically indexed kernel parameter would be copied to local memory)
+        const int own_W = s == 0 ? lg.w[0] : s == 1 ? lg.w[1] : s == 2 ? lg.w[2] : lg.w[3];
+        const int own_H = s == 0 ? lg.h[0] : s == 1 ? lg.h[1] : s == 2 ? lg.h[2] : lg.h[3];
         const float* qp = qproj + (int64_t)q * 768;
         float offn[16], wl[8];
         {
             const float4* o4 = reinterpret_cast<const float4*>(qp + head * 64 + s * 16);
-            const float fw = (float)lg.w[s], fh = (float)lg.h[s];
+            const float fw = (float)own_W, fh = (float)own_H;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float4 t = __ldg(o4 + i);
@@ -261,39 +326,38 @@ sca_fused_kernel(const T* __restrict__ value, const float* __restrict__ qproj, S
 #pragma unroll
             for (int i = 0; i < 8; ++i) wl[i] = wl[i] / sum;
         }
-        const float own_w = (float)lg.w[s], own_h = (float)lg.h[s];
+        const float own_w = (float)own_W, own_h = (float)own_H;
         const int grp = lane & ~3;
         for (int c = 0; c < sp.num_cams; ++c) {
             if (!((vis >> c) & 1u)) continue;                            // warp-uniform
             const int r = c >> 2;
-            // sampling location of point p uses pillar anchor p % D (Z-anchor interleave, :366-373)
-            float wim[8], him[8];
+            const T* vcam = value + ((int64_t)c * Nv * 8 + head) * 32 + s * 8;
 #pragma unroll
             for (int p = 0; p < 8; ++p) {
-                const int src = (c & 3) * 8 + (p % sp.D);
-                const float u = __shfl_sync(FULL, r ? ru[1] : ru[0], src);
-                const float v = __shfl_sync(FULL, r ? rv[1] : rv[0], src);
-                wim[p] = __fadd_rn(u, offn[2 * p]) * own_w - 0.5f;
-                him[p] = __fadd_rn(v, offn[2 * p + 1]) * own_h - 0.5f;
-            }
-            const T* vcam = value + ((int64_t)c * Nv * 8 + head) * 32 + s * 8;
-            for (int l = 0; l < 4; ++l) {
-                const int src = grp | l;
-                const T* base = vcam + (int64_t)lg.start[l] * 256;
-                const int H = lg.h[l], W = lg.w[l];
+                // sampling location of point p uses pillar anchor p % D (Z-anchor interleave, :366-373)
+                const int asrc = (c & 3) * 8 + (p % sp.D);
+                const float u = __shfl_sync(FULL, r ? ru[1] : ru[0], asrc);
+                const float v = __shfl_sync(FULL, r ? rv[1] : rv[0], asrc);
+                const float w_im = __fadd_rn(u, offn[2 * p]) * own_w - 0.5f;
+                const float h_im = __fadd_rn(v, offn[2 * p + 1]) * own_h - 0.5f;
+                const SamplePrep sm = prep_sample(h_im, w_im, wl[p], own_H, own_W);   // my (head, level s, point p)
 #pragma unroll
-                for (int p = 0; p < 8; ++p) {
-                    const float w_im = __shfl_sync(FULL, wim[p], src);
-                    const float h_im = __shfl_sync(FULL, him[p], src);
-                    const float wt = __shfl_sync(FULL, wl[p], src);
-                    bilinear_acc8<T>(base, H, W, 256, h_im, w_im, wt, acc);
+                for (int l = 0; l < 4; ++l) {
+                    const int src = grp | l;
+                    const int code = __shfl_sync(FULL, sm.code, src);
+                    const float c1 = __shfl_sync(FULL, sm.c1, src), c2 = __shfl_sync(FULL, sm.c2, src);
+                    const float c3 = __shfl_sync(FULL, sm.c3, src), c4 = __shfl_sync(FULL, sm.c4, src);
+                    gather_sample<T>(vcam + (int64_t)lg.start[l] * 256, lg.w[l], code, c1, c2, c3, c4, acc2);
                 }
             }
         }
         const float cnt = (float)count;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = __fdiv_rn(acc[i], cnt);
+        for (int i = 0; i < 4; ++i) { acc2[i].x = __fdiv_rn(acc2[i].x, cnt); acc2[i].y = __fdiv_rn(acc2[i].y, cnt); }
     }
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc[2 * i] = acc2[i].x; acc[2 * i + 1] = acc2[i].y; }
     store8(out + (int64_t)q * 256 + head * 32 + s * 8, acc);
 }
 

@@ -391,11 +391,12 @@ def test_ray_metric_counters_match_oracle(f64, golden_dir):
     assert torch.equal(before, rm.counters)
 
 
-def test_full_size_properties_bf16():
+@pytest.mark.parametrize('tc', [False, True])
+def test_full_size_properties_bf16(tc):
     """BASELINE full sizes, size-independent properties: determinism (bit-identical reruns), argmax consistent with
-    the engine's own logits, per-query independence from unrelated camera content."""
+    the engine's own logits, finite outputs; tensor-core and CUDA-core bf16 paths agree with each other."""
     cfg, params, feats, metas, _ = make_case('full', num_layers=2)
-    eng = engine_for(cfg, params, metas, 'bf16')
+    eng = engine_for(cfg, params, metas, 'bf16', tc=tc)
     fd = [f[0].to(DEV) for f in feats]
     a = eng.forward(fd, want=('bev_embed', 'occ', 'occ_cls', 'flow'))
     a = {k: v.clone() for k, v in a.items()}
@@ -405,3 +406,8 @@ def test_full_size_properties_bf16():
     assert torch.equal(a['occ'].argmax(-1).to(torch.uint8), a['occ_cls'])
     assert torch.isfinite(a['bev_embed']).all() and torch.isfinite(a['occ']).all()
     assert eng.launches_per_frame > 20
+    if tc:
+        ref = engine_for(cfg, params, metas, 'bf16', tc=False).forward(fd, want=('bev_embed', 'occ', 'occ_cls', 'flow'))
+        assert (a['bev_embed'] - ref['bev_embed']).abs().max().item() < 8e-2       # bf16 weights vs fp32 weights
+        assert (a['occ'] - ref['occ']).abs().max().item() < 8e-2
+        assert (a['occ_cls'] == ref['occ_cls']).float().mean().item() > 0.97
