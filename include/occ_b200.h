@@ -99,6 +99,15 @@ int occb200_engine_forward(occb200_engine* e, const float* const* feats, const f
 int occb200_engine_forward_host(occb200_engine* e, const float* const* feats_host, int64_t* occ_cls_i64_host,
                                 float* flow_host, void* stream);
 
+/* Pipelined form of the same call for streams of frames: _submit_host enqueues the host->device copy of the
+ * frame's features (copy stream), the frame (caller's stream, after that copy) and the device->host copy of the
+ * results (second copy stream) for `slot` in {0,1} and returns; _wait_host blocks until the slot's results are in
+ * the host buffers.  With two slots in flight the copies of frame i+1 / i-1 overlap the compute of frame i.
+ * Host buffers must be pinned for the copies to be asynchronous. */
+int occb200_engine_submit_host(occb200_engine* e, int slot, const float* const* feats_host, int64_t* occ_cls_i64_host,
+                               float* flow_host, void* stream);
+int occb200_engine_wait_host(occb200_engine* e, int slot);
+
 /* Intermediate taps for parity tests (dev f32, valid after a forward; NULL if not produced):
  *   which: 0 = layer output [Nq,C] of layer `layer`; 1 = TSA output (pre-norm, with residual); 2 = SCA output
  *   (pre-norm, with residual); 3 = voxel features [X,Y,Z,out_dim] (converted to fp32 into `dst`). */

@@ -8,7 +8,8 @@
 // im2col is done by TMA: one 4-D box load {Cin, 16 z, 8 y, 1 x} per tap with the tap's (dz,dy,dx) offset
 // in the coordinates; out-of-bounds rows are zero-filled by the TMA unit, which IS the conv's zero padding
 // (including the z = -1 / z = 16 halo).  All 27 weight tiles stay resident in shared memory.
-//   warp 0: TMA producer (8-stage ring)    warp 1: tcgen05.mma issuer (accumulator double-buffered in TMEM)
+//   warp 0: TMA producer (8-stage ring)    warp 1: tcgen05.mma issuer (plane-major: each loaded tile feeds the
+//   dx = 0/1/2 taps of three neighbouring outputs, whose accumulators live in 4 TMEM slots)
 //   warps 2-5: epilogue (tcgen05.ld -> +bias -> ReLU -> bf16 -> 64-byte rows, contiguous 8 KB per tile)
 #include "common.cuh"
 #include "conv3d_tc.cuh"
@@ -18,9 +19,14 @@ namespace occ {
 
 namespace {
 
-constexpr int STAGES = 8, TILE_Y = 8, TILE_Z = 16, BLOCK_M = 128, COUT = 32, TAPS = 27;
+constexpr int STAGES = 8, TILE_Y = 8, TILE_Z = 16, BLOCK_M = 128, COUT = 32, TAPS = 27, SLOTS = 4;
 constexpr int NUM_THREADS = 192;
 
+// Plane-major schedule: an input tile (plane x = p, shift (dz,dy)) is the A operand of three taps -- dx = 0, 1, 2 of
+// the outputs x = p+1, p, p-1 -- so it is loaded ONCE and multiplied into three live accumulators (4 TMEM slots of
+// 32 columns).  L2->SMEM traffic drops from 27 to ~9 tile loads per output tile.  Each CTA owns a contiguous range
+// of the (y_tile, x) tile sequence, cut into segments of constant y_tile; a segment [xa, xb) streams the planes
+// max(xa-1,0) .. min(xb, X-1).
 template <int CIN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
@@ -37,22 +43,23 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
     auto full_bar = [&](int s) { return bar_base + s * 8; };
     auto empty_bar = [&](int s) { return bar_base + (STAGES + s) * 8; };
     auto tfull_bar = [&](int s) { return bar_base + (2 * STAGES + s) * 8; };
-    auto tempty_bar = [&](int s) { return bar_base + (2 * STAGES + 2 + s) * 8; };
-    const uint32_t w_bar = bar_base + (2 * STAGES + 4) * 8;
-    const uint32_t tmem_slot = bar_base + (2 * STAGES + 5) * 8;
+    auto tempty_bar = [&](int s) { return bar_base + (2 * STAGES + SLOTS + s) * 8; };
+    const uint32_t w_bar = bar_base + (2 * STAGES + 2 * SLOTS) * 8;
+    const uint32_t tmem_slot = bar_base + (2 * STAGES + 2 * SLOTS + 1) * 8;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int y_tiles = (Y + TILE_Y - 1) / TILE_Y;
-    const int num_tiles = X * y_tiles;
+    const long long total = (long long)X * y_tiles;
+    const int t_begin = (int)(total * blockIdx.x / gridDim.x), t_end = (int)(total * (blockIdx.x + 1) / gridDim.x);
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmIn); tc::tma_prefetch_desc(&tmW);
         for (int s = 0; s < STAGES; ++s) { tc::mbar_init(full_bar(s), 1); tc::mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; ++s) { tc::mbar_init(tfull_bar(s), 1); tc::mbar_init(tempty_bar(s), 128); }
+        for (int s = 0; s < SLOTS; ++s) { tc::mbar_init(tfull_bar(s), 1); tc::mbar_init(tempty_bar(s), 128); }
         tc::mbar_init(w_bar, 1);
         tc::mbar_fence_init();
     }
-    if (warp == 1) tc::tmem_alloc(tmem_slot, 64);
+    if (warp == 1) tc::tmem_alloc(tmem_slot, 32 * SLOTS);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -64,57 +71,79 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
             tc::mbar_arrive_expect_tx(w_bar, TAPS * W_TAP_BYTES);
             for (int t = 0; t < TAPS; ++t) tc::tma_load_2d(w_base + t * W_TAP_BYTES, &tmW, w_bar, 0, t * COUT);
             int s = 0; uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int x = tile / y_tiles, y0 = (tile % y_tiles) * TILE_Y;
-                for (int t = 0; t < TAPS; ++t) {
-                    const int dz = t / 9, dy = (t / 3) % 3, dx = t % 3;
-                    tc::mbar_wait(empty_bar(s), ph ^ 1);
-                    tc::mbar_arrive_expect_tx(full_bar(s), A_BYTES);
-                    tc::tma_load_4d(a_base + s * A_BYTES, &tmIn, full_bar(s), 0, dz - 1, y0 + dy - 1, x + dx - 1);
-                    if (++s == STAGES) { s = 0; ph ^= 1; }
+            for (int t = t_begin; t < t_end;) {
+                const int yt = t / X, xa = t % X;
+                const int xb = min(X, xa + (t_end - t));
+                const int y0 = yt * TILE_Y;
+                const int p_lo = max(xa - 1, 0), p_hi = min(xb, X - 1);
+                for (int p = p_lo; p <= p_hi; ++p) {
+                    for (int t9 = 0; t9 < 9; ++t9) {
+                        const int dz = t9 / 3, dy = t9 % 3;
+                        tc::mbar_wait(empty_bar(s), ph ^ 1);
+                        tc::mbar_arrive_expect_tx(full_bar(s), A_BYTES);
+                        tc::tma_load_4d(a_base + s * A_BYTES, &tmIn, full_bar(s), 0, dz - 1, y0 + dy - 1, p);
+                        if (++s == STAGES) { s = 0; ph ^= 1; }
+                    }
                 }
+                t += xb - xa;
             }
         }
     } else if (warp == 1) {
-        const uint32_t idesc = tc::make_idesc_bf16(BLOCK_M, COUT);
-        int s = 0; uint32_t ph = 0; int as = 0; uint32_t aph = 0;
-        if (lane == 0) { tc::mbar_wait(w_bar, 0); tc::tc_fence_after(); }
-        __syncwarp();
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            if (lane == 0) { tc::mbar_wait(tempty_bar(as), aph ^ 1); tc::tc_fence_after(); }
-            __syncwarp();
-            for (int t = 0; t < TAPS; ++t) {
-                if (lane == 0) {
-                    tc::mbar_wait(full_bar(s), ph);
-                    tc::tc_fence_after();
-                    const uint64_t da = tc::make_smem_desc(a_base + s * A_BYTES, ROW_BYTES);
-                    const uint64_t db = tc::make_smem_desc(w_base + t * W_TAP_BYTES, ROW_BYTES);
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc_bf16(BLOCK_M, COUT);
+            int s = 0; uint32_t ph = 0;
+            int n_base = 0;
+            tc::mbar_wait(w_bar, 0);
+            tc::tc_fence_after();
+            for (int t = t_begin; t < t_end;) {
+                const int xa = t % X;
+                const int xb = min(X, xa + (t_end - t));
+                const int p_lo = max(xa - 1, 0), p_hi = min(xb, X - 1);
+                for (int p = p_lo; p <= p_hi; ++p) {
+                    for (int t9 = 0; t9 < 9; ++t9) {
+                        tc::mbar_wait(full_bar(s), ph);
+                        tc::tc_fence_after();
+                        const uint64_t da = tc::make_smem_desc(a_base + s * A_BYTES, ROW_BYTES);
 #pragma unroll
-                    for (int k = 0; k < CIN / 16; ++k)
-                        tc::umma_bf16(tmem_base + as * 32, da + 2 * k, db + 2 * k, idesc, (t | k) != 0);
-                    tc::umma_commit(empty_bar(s));
-                    if (t == TAPS - 1) tc::umma_commit(tfull_bar(as));
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const int x = p - dx + 1;                       // the output this tile feeds through tap dx
+                            if (x < xa || x >= xb) continue;
+                            const int n = n_base + (x - xa), slot = n & (SLOTS - 1);
+                            const bool opens = (t9 == 0) && (p == max(x - 1, 0));
+                            if (opens) {                                    // accumulator slot must have been drained
+                                tc::mbar_wait(tempty_bar(slot), ((n / SLOTS) & 1) ^ 1);
+                                tc::tc_fence_after();
+                            }
+                            const uint64_t db = tc::make_smem_desc(w_base + (t9 * 3 + dx) * W_TAP_BYTES, ROW_BYTES);
+#pragma unroll
+                            for (int k = 0; k < CIN / 16; ++k)
+                                tc::umma_bf16(tmem_base + slot * 32, da + 2 * k, db + 2 * k, idesc, !(opens && k == 0));
+                            if (t9 == 8 && p == min(x + 1, X - 1)) tc::umma_commit(tfull_bar(slot));   // output complete
+                        }
+                        tc::umma_commit(empty_bar(s));
+                        if (++s == STAGES) { s = 0; ph ^= 1; }
+                    }
                 }
-                __syncwarp();
-                if (++s == STAGES) { s = 0; ph ^= 1; }
+                n_base += xb - xa;
+                t += xb - xa;
             }
-            if (++as == 2) { as = 0; aph ^= 1; }
         }
     } else {
         const int quarter = warp & 3;
-        int as = 0; uint32_t aph = 0;
         float b[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) b[i] = __ldg(bias + i);
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int x = tile / y_tiles, y0 = (tile % y_tiles) * TILE_Y;
-            tc::mbar_wait(tfull_bar(as), aph);
+        int n = 0;
+        for (int t = t_begin; t < t_end; ++t, ++n) {
+            const int x = t % X, y0 = (t / X) * TILE_Y;
+            const int slot = n & (SLOTS - 1);
+            tc::mbar_wait(tfull_bar(slot), (n / SLOTS) & 1);
             tc::tc_fence_after();
             uint32_t r[32];
-            tc::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + as * 32, r);
+            tc::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * 32, r);
             tc::tmem_ld_wait();
             tc::tc_fence_before();
-            tc::mbar_arrive(tempty_bar(as));                 // accumulator is in registers: release TMEM early
+            tc::mbar_arrive(tempty_bar(slot));               // accumulator is in registers: release TMEM early
             const int row = quarter * 32 + lane;
             const int y = y0 + row / TILE_Z, z = row % TILE_Z;
             if (y < Y) {
@@ -130,14 +159,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
                     op[i] = u;
                 }
             }
-            if (++as == 2) { as = 0; aph ^= 1; }
         }
     }
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc::tc_fence_after();
-        tc::tmem_dealloc(tmem_base, 64);
+        tc::tmem_dealloc(tmem_base, 32 * SLOTS);
     }
 }
 

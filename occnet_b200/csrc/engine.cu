@@ -66,6 +66,7 @@ struct occb200_engine {
     std::vector<LayerW> layers;
     DevBuf bev_queries, pos, cams_embeds, level_embeds;
     DevBuf conv_w[2], conv_b[2], conv_wh[2];
+    DevBuf sca_v_all_wh, sca_v_all_b, sca_value_all;     // value_proj of every layer, concatenated (tensor-core path)
     DevBuf hw1, hb1, hw2, hb2, fw1, fb1, fw2, fb2, head_w1h, head_w2h, head_b1c, head_b2c;
     // workspace
     DevBuf tokens, sca_value, q_f32, q_t, q_pos_t, q0_t, prev_t, tsa_value, tsa_value_prev, qproj, attn_out, x_f32,
@@ -73,6 +74,13 @@ struct occb200_engine {
     DevBuf tap_layer, tap_tsa, tap_sca;
     // host-buffer variant
     DevBuf feats_dev[4], occ_i64_dev, flow_dev;
+    // pipelined host-buffer variant: 2 slots, copies on their own streams, compute on the caller's stream
+    struct Slot {
+        DevBuf feats[4], occ, flow;
+        cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
+        bool busy = false;
+    } slots[2];
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     int launches = 0;
     // optional per-kernel-category timing (CUDA events on the launch stream)
     bool profiling = false;
@@ -196,6 +204,13 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
     }
     float* qproj = e->qproj.as<float>();
     T* attn_out = e->attn_out.as<T>();
+    const bool hoist_v = sizeof(T) == 2 && c.use_tensor_cores && e->sca_value_all.p != nullptr;
+    if (hoist_v) {
+        e->launches++;
+        ProfScope ps(e, st, CAT_GEMM);
+        if (gemm_tc_blocked256((const bf16*)tokens, e->sca_v_all_wh.as<bf16>(), e->sca_v_all_b.as<float>(),
+                               e->sca_value_all.as<bf16>(), ncam * Nv, c.num_layers * C, C, st)) return 2;
+    }
     for (int l = 0; l < c.num_layers; ++l) {
         LayerW& w = e->layers[l];
         // ---- temporal self-attention (temporal_self_attention.py:177-272)
@@ -238,12 +253,14 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
         const int nq_sca = 8 * c.num_levels * c.sca_points * 3;
         if (gemm<T, float>(e, q_t, nullptr, 0, w.sca_q_w.as<float>(), w.sca_q_wh.p, w.sca_q_b.as<float>(), nullptr,
                            qproj, Nq, nq_sca, C, ACT_NONE, st)) return 2;
-        if (gemm<T, T>(e, tokens, nullptr, 0, w.sca_v_w.as<float>(), w.sca_v_wh.p, w.sca_v_b.as<float>(), nullptr,
-                       e->sca_value.as<T>(), ncam * Nv, C, C, ACT_NONE, st)) return 2;
+        const T* sca_val = e->sca_value.as<T>();
+        if (hoist_v) {
+            sca_val = reinterpret_cast<const T*>(e->sca_value_all.as<bf16>() + (size_t)l * ncam * Nv * C);
+        } else if (gemm<T, T>(e, tokens, nullptr, 0, w.sca_v_w.as<float>(), w.sca_v_wh.p, w.sca_v_b.as<float>(), nullptr,
+                              e->sca_value.as<T>(), ncam * Nv, C, C, ACT_NONE, st)) return 2;
         {
             ProfScope ps(e, st, CAT_SCA);
-            if (launch_sca_fused<T>(e->sca_value.as<T>(), qproj, e->sp, e->lg, Nv, attn_out, e->hits.as<uint8_t>(), st))
-                return 2;
+            if (launch_sca_fused<T>(sca_val, qproj, e->sp, e->lg, Nv, attn_out, e->hits.as<uint8_t>(), st)) return 2;
         }
         e->launches++;
         if (fuse_ln) {
@@ -390,13 +407,20 @@ void occb200_engine_destroy(occb200_engine* e)
         for (DevBuf* b : all) b->release();
     }
     DevBuf* all[] = {&e->bev_queries, &e->pos, &e->cams_embeds, &e->level_embeds, &e->conv_w[0], &e->conv_w[1],
-                     &e->conv_b[0], &e->conv_b[1], &e->conv_wh[0], &e->conv_wh[1], &e->hw1, &e->hb1, &e->hw2, &e->hb2,
+                     &e->conv_b[0], &e->conv_b[1], &e->conv_wh[0], &e->conv_wh[1], &e->sca_v_all_wh, &e->sca_v_all_b, &e->sca_value_all, &e->hw1, &e->hb1, &e->hw2, &e->hb2,
                      &e->fw1, &e->fb1, &e->fw2, &e->fb2, &e->head_w1h, &e->head_w2h, &e->head_b1c, &e->head_b2c, &e->tokens, &e->sca_value, &e->q_f32, &e->q_t,
                      &e->q_pos_t, &e->q0_t, &e->prev_t, &e->tsa_value, &e->tsa_value_prev, &e->qproj, &e->attn_out,
                      &e->x_f32, &e->ffn_h, &e->vox0, &e->vox1, &e->vox2, &e->hits, &e->tap_layer, &e->tap_tsa,
                      &e->tap_sca, &e->feats_dev[0], &e->feats_dev[1], &e->feats_dev[2], &e->feats_dev[3],
                      &e->occ_i64_dev, &e->flow_dev};
     for (DevBuf* b : all) b->release();
+    for (auto& sl : e->slots) {
+        for (auto& f : sl.feats) f.release();
+        sl.occ.release(); sl.flow.release();
+        if (sl.h2d_done) { cudaEventDestroy(sl.h2d_done); cudaEventDestroy(sl.compute_done); cudaEventDestroy(sl.d2h_done); }
+    }
+    if (e->h2d_stream) { cudaStreamDestroy(e->h2d_stream); cudaStreamDestroy(e->d2h_stream); }
+    for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
     delete e;
 }
 
@@ -480,6 +504,21 @@ int occb200_engine_finalize(occb200_engine* e)
             GETP(b, pre + ".norms." + std::to_string(n) + ".bias", (size_t)C);
             if (upload(w.ln_g[n], g->data(), C) || upload(w.ln_b[n], b->data(), C)) return 2;
         }
+    }
+    if (tc) {
+        // SpatialCrossAttention's value_proj input (the camera tokens) does not depend on the layer
+        // (spatial_cross_attention.py:334): project once with all layers' weights, [L*256, 256].
+        std::vector<float> W, B;
+        for (int l = 0; l < c.num_layers; ++l) {
+            const std::string d = "transformer.encoder.layers." + std::to_string(l) + ".attentions.1.deformable_attention.value_proj";
+            const std::vector<float>* w = find(e, d + ".weight", (size_t)C * C);
+            const std::vector<float>* b = find(e, d + ".bias", (size_t)C);
+            if (!w || !b) return 3;
+            W.insert(W.end(), w->begin(), w->end());
+            B.insert(B.end(), b->begin(), b->end());
+        }
+        if (upload_bf16(e->sca_v_all_wh, W.data(), W.size()) || upload(e->sca_v_all_b, B.data(), B.size())) return 2;
+        if (e->sca_value_all.alloc((size_t)c.num_layers * c.num_cams * e->Nv * C * 2)) return 2;
     }
     // decoder: fold BatchNorm3d (eval) into the conv weights; torch layout [Cout][Cin][kz][ky][kx] -> [tap][Cin][Cout]
     for (int i = 0; i < 2; ++i) {
@@ -607,6 +646,59 @@ int occb200_engine_forward_host(occb200_engine* e, const float* const* feats_hos
     OCC_CUDA(cudaMemcpyAsync(occ_cls_i64_host, e->occ_i64_dev.p, nvox * 8, cudaMemcpyDeviceToHost, st));
     OCC_CUDA(cudaMemcpyAsync(flow_host, e->flow_dev.p, nvox * 8, cudaMemcpyDeviceToHost, st));
     OCC_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int occb200_engine_submit_host(occb200_engine* e, int slot, const float* const* feats_host, int64_t* occ_cls_i64_host,
+                               float* flow_host, void* stream)
+{
+    OCC_CHECK(e && feats_host && occ_cls_i64_host && flow_host, "null pointer");
+    OCC_CHECK(slot == 0 || slot == 1, "slot must be 0 or 1");
+    OCC_CHECK(e->finalized && e->cameras_set, "engine not finalized / cameras not set");
+    const occb200_config& c = e->cfg;
+    cudaStream_t st = (cudaStream_t)stream;
+    occb200_engine::Slot& s = e->slots[slot];
+    OCC_CHECK(!s.busy, "slot still in flight: call occb200_engine_wait_host first");
+    if (!e->h2d_stream) {
+        OCC_CUDA(cudaStreamCreateWithFlags(&e->h2d_stream, cudaStreamNonBlocking));
+        OCC_CUDA(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
+    }
+    if (!s.h2d_done) {
+        OCC_CUDA(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
+        OCC_CUDA(cudaEventCreateWithFlags(&s.compute_done, cudaEventDisableTiming));
+        OCC_CUDA(cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming));
+    }
+    const size_t nvox = (size_t)c.bev_w * c.bev_h * c.pillar_h;
+    const float* dev_feats[4];
+    for (int l = 0; l < 4; ++l) {
+        const size_t n = (size_t)c.num_cams * 256 * e->lg.h[l] * e->lg.w[l] * 4;
+        if (s.feats[l].bytes != n && s.feats[l].alloc(n)) return 2;
+        OCC_CUDA(cudaMemcpyAsync(s.feats[l].p, feats_host[l], n, cudaMemcpyHostToDevice, e->h2d_stream));
+        dev_feats[l] = s.feats[l].as<float>();
+    }
+    OCC_CUDA(cudaEventRecord(s.h2d_done, e->h2d_stream));
+    if (s.occ.bytes != nvox * 8 && s.occ.alloc(nvox * 8)) return 2;
+    if (s.flow.bytes != nvox * 8 && s.flow.alloc(nvox * 8)) return 2;
+    OCC_CUDA(cudaStreamWaitEvent(st, s.h2d_done, 0));              // compute waits for this frame's features only
+    int rc = occb200_engine_forward(e, dev_feats, nullptr, nullptr, nullptr, s.flow.as<float>(), nullptr,
+                                    s.occ.as<int64_t>(), stream);
+    if (rc) return rc;
+    OCC_CUDA(cudaEventRecord(s.compute_done, st));
+    OCC_CUDA(cudaStreamWaitEvent(e->d2h_stream, s.compute_done, 0));
+    OCC_CUDA(cudaMemcpyAsync(occ_cls_i64_host, s.occ.p, nvox * 8, cudaMemcpyDeviceToHost, e->d2h_stream));
+    OCC_CUDA(cudaMemcpyAsync(flow_host, s.flow.p, nvox * 8, cudaMemcpyDeviceToHost, e->d2h_stream));
+    OCC_CUDA(cudaEventRecord(s.d2h_done, e->d2h_stream));
+    s.busy = true;
+    return 0;
+}
+
+int occb200_engine_wait_host(occb200_engine* e, int slot)
+{
+    OCC_CHECK(e && (slot == 0 || slot == 1), "bad arguments");
+    occb200_engine::Slot& s = e->slots[slot];
+    if (!s.busy) return 0;
+    OCC_CUDA(cudaEventSynchronize(s.d2h_done));
+    s.busy = false;
     return 0;
 }
 

@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmW, const float* __restrict__ bias,
                const float* __restrict__ residual, TC* __restrict__ C, LnArgs ln, int M, int N, int BN, int nk,
-               int nk1, int act, int w_resident, int stages, long long* __restrict__ dbg)
+               int nk1, int act, int w_resident, int stages, long long ldc, long long nblk_stride,
+               long long* __restrict__ dbg)
 {
     // optional in-kernel timeline (globaltimer ns): 16 slots per CTA, written by the role that owns the event
     auto stamp = [&](int slot) {
@@ -321,7 +322,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (act == ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                         if (residual) { const float4 q = pre[i]; v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
                         if (grow < M) {
-                            const size_t o = (size_t)grow * N + col + cpiece * 4;
+                            // default (ldc = N, nblk_stride = BN) is the plain row-major [M,N]; the blocked form
+                            // writes each n-block as its own contiguous [M,BN] matrix (per-layer value buffers)
+                            const size_t o = (size_t)n_blk * nblk_stride + (size_t)grow * ldc + c0 + cpiece * 4;
                             if constexpr (sizeof(TC) == 4) *reinterpret_cast<float4*>(reinterpret_cast<float*>(C) + o) = v;
                             else *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(C) + o) =
                                      make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
@@ -403,7 +406,7 @@ int cached_map_2d(const void* base, uint64_t inner, uint64_t rows, uint32_t box_
 
 template <typename TC, bool LN>
 int launch(const bf16* A, const bf16* A2, int K1, const bf16* W, const float* bias, const float* residual, TC* C,
-           LnArgs ln, int M, int N, int K, int act, cudaStream_t stream)
+           LnArgs ln, int M, int N, int K, int act, cudaStream_t stream, bool blocked_out = false)
 {
     if (A2 == nullptr) K1 = K;
     const Plan p = make_plan(N, K, LN);
@@ -435,7 +438,9 @@ int launch(const bf16* A, const bf16* A2, int K1, const bf16* W, const float* bi
         OCC_CUDA(cudaMemsetAsync(dbg, 0, (size_t)grid * 16 * sizeof(long long), stream));
     }
     gemm_tc_kernel<TC, LN><<<grid, NUM_THREADS, p.smem, stream>>>(tmA, tmA2, tmW, bias, residual, C, ln, M, N, p.BN,
-                                                                 K / BLOCK_K, K1 / BLOCK_K, act, p.resident, p.stages, dbg);
+                                                                 K / BLOCK_K, K1 / BLOCK_K, act, p.resident, p.stages,
+                                                                 blocked_out ? (long long)p.BN : (long long)N,
+                                                                 blocked_out ? (long long)M * p.BN : (long long)p.BN, dbg);
     OCC_CUDA(cudaGetLastError());
     if (want_dbg) {                                               // development aid: per-CTA timeline in ns
         std::vector<long long> h((size_t)grid * 16);
@@ -469,6 +474,13 @@ int gemm_tc(const bf16* A, const bf16* A2, int K1, const bf16* W, const float* b
             int M, int N, int K, int act, cudaStream_t stream)
 {
     return launch<TC, false>(A, A2, K1, W, bias, residual, C, LnArgs{}, M, N, K, act, stream);
+}
+
+int gemm_tc_blocked256(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, int N, int K, cudaStream_t stream)
+{
+    const Plan p = make_plan(N, K, false);
+    OCC_CHECK(p.BN == 256 && N % 256 == 0, "gemm_tc_blocked256: N must be a multiple of 256 with 256-wide tiles");
+    return launch<bf16, false>(A, nullptr, 0, W, bias, nullptr, C, LnArgs{}, M, N, K, ACT_NONE, stream, true);
 }
 
 int gemm_tc_ln(const bf16* A, const bf16* W, const float* bias, const float* residual, const float* gamma,

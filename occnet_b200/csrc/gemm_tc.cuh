@@ -17,6 +17,10 @@ int gemm_tc_ln(const bf16* A, const bf16* W, const float* bias, const float* res
                const float* beta, const float* pos, float* y_f32, bf16* y_bf16, bf16* y_pos_bf16, int M, int K,
                cudaStream_t stream);
 
+// C = A.W^T + bias with N = n*256: output written as n separate contiguous [M,256] bf16 matrices (C + i*M*256).
+// Used to project the camera tokens with the value_proj weights of ALL encoder layers in one pass over the tokens.
+int gemm_tc_blocked256(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, int N, int K, cudaStream_t stream);
+
 int launch_bf16_to_f32(const bf16* src, float* dst, int64_t n, cudaStream_t stream);
 
 }  // namespace occ

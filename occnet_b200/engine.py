@@ -129,6 +129,40 @@ class OccEngine:
                                                             _lib.stream_ptr()))
         return occ_out, flow_out
 
+    def submit_host(self, slot, feats_host, occ_out, flow_out):
+        """Pipelined host-buffer call (slot 0/1): returns immediately; `wait_host(slot)` completes it."""
+        arr = (ctypes.c_void_p * 4)()
+        for i, f in enumerate(feats_host):
+            assert not f.is_cuda and f.dtype == torch.float32 and f.is_contiguous()
+            arr[i] = f.data_ptr()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.occb200_engine_submit_host(self._h, slot, arr, _lib.ptr(occ_out), _lib.ptr(flow_out),
+                                                           _lib.stream_ptr()))
+
+    def wait_host(self, slot):
+        _lib.check(self.lib.occb200_engine_wait_host(self._h, slot))
+
+    def stream_host(self, frames_host):
+        """Generator over an iterable of host frames with two frames in flight; yields (occ int64 CPU, flow CPU)
+        views of the slot's pinned output buffers (valid until the slot is reused two frames later)."""
+        X, Y, Z = self.vox_shape
+        if getattr(self, '_stream_outs', None) is None:              # pinned once: cudaHostAlloc costs milliseconds
+            self._stream_outs = [(torch.empty((X, Y, Z), dtype=torch.int64).pin_memory(),
+                                  torch.empty((X, Y, Z, 2)).pin_memory()) for _ in range(2)]
+        outs = self._stream_outs
+        pending = []
+        for i, fr in enumerate(frames_host):
+            slot = i & 1
+            if len(pending) == 2:
+                s = pending.pop(0)
+                self.wait_host(s)
+                yield outs[s]
+            self.submit_host(slot, fr, *outs[slot])
+            pending.append(slot)
+        for s in pending:
+            self.wait_host(s)
+            yield outs[s]
+
     def enable_taps(self, on=True):
         _lib.check(self.lib.occb200_engine_enable_taps(self._h, int(on)))
 

@@ -85,7 +85,10 @@ def finalize_counters(v):
     with np.errstate(divide='ignore', invalid='ignore'):
         iou = np.stack([(tp[j] / (gt + pred - tp[j]))[:-1] for j in range(3)])
         ave_l = ave[1][:-1] / ave_count[1][:-1]
-        miou = np.nanmean(iou)
-        mave = np.nanmean(ave_l)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore', RuntimeWarning)          # all-NaN slices (classes absent from the fixture)
+            miou = np.nanmean(iou)
+            mave = np.nanmean(ave_l)
     score = miou * 0.9 + max(1 - mave, 0.0) * 0.1
     return dict(iou=iou, ave=ave_l, miou=float(miou), mave=float(mave), score=float(score))

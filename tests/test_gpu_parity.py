@@ -277,6 +277,22 @@ def test_forward_host_equals_device_path():
     assert torch.equal(flow_h, out['flow'].cpu())
 
 
+def test_pipelined_host_stream_equals_sync_calls():
+    """submit/wait with two frames in flight returns exactly what the synchronous host call returns, frame by frame."""
+    cfg, params, _, metas, _ = make_case('small6')
+    eng = engine_for(cfg, params, metas, 'fp32')
+    frames = [[f[0].contiguous().pin_memory() for f in fixtures.make_feats(cfg, bs=1, seed=50 + i)] for i in range(5)]
+    want = []
+    for fr in frames:
+        o, f = eng.forward_host(fr)
+        want.append((o.clone(), f.clone()))
+    got = [(o.clone(), f.clone()) for o, f in eng.stream_host(frames)]
+    assert len(got) == 5
+    for (go, gf), (wo, wf) in zip(got, want):
+        assert torch.equal(go, wo) and torch.equal(gf, wf)
+    assert not torch.equal(want[0][1], want[1][1])               # the frames really differ
+
+
 # ------------------------------------------------------------------------------------------ metric (a14, a15)
 def _metric_fixture():
     sem_gt, flow_gt = fixtures.make_occ_scene(seed=4)
