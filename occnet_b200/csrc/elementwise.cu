@@ -7,34 +7,48 @@ namespace occ {
 
 namespace {
 
-// [cam][C][hw] f32 -> [cam][Nv][C] T (+ cams_embeds[cam][c], then + level_embed[c]; same order as the reference)
+// [cam][C][hw] f32 -> [cam][Nv][C] T (+ cams_embeds[cam][c], then + level_embed[c]; same order as the reference).
+// 64 (pixels) x 64 (channels) tile per CTA: float4 reads along the pixel axis, 16-byte (8 x bf16) writes along C.
 template <typename T>
-__global__ void pack_level_kernel(const float* __restrict__ feat, const float* __restrict__ cams_embeds,
-                                  const float* __restrict__ level_embed, int C, int hw, int Nv, int start,
-                                  T* __restrict__ tokens)
+__global__ void __launch_bounds__(256)
+pack_level_kernel(const float* __restrict__ feat, const float* __restrict__ cams_embeds,
+                  const float* __restrict__ level_embed, int C, int hw, int Nv, int start, T* __restrict__ tokens)
 {
-    __shared__ float tile[32][33];
+    __shared__ float tile[64][65];                             // [channel][pixel], padded
     const int cam = blockIdx.z;
-    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-    const int tx = threadIdx.x, ty = threadIdx.y;                 // 32 x 8
+    const int p0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+    const int tid = threadIdx.x;
     const float* src = feat + (int64_t)cam * C * hw;
+    const bool vec_ok = (hw & 3) == 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int c = c0 + ty + i * 8, p = p0 + tx;
-        tile[ty + i * 8][tx] = (p < hw) ? __ldg(src + (int64_t)c * hw + p) : 0.f;
+    for (int i = 0; i < 4; ++i) {                              // 64 channels x 16 float4 = 1024 float4, 4 per thread
+        const int idx = tid + i * 256;
+        const int c = idx >> 4, p4 = (idx & 15) * 4;
+        const float* sp = src + (int64_t)(c0 + c) * hw + p0 + p4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vec_ok && p0 + p4 + 3 < hw) v = __ldg(reinterpret_cast<const float4*>(sp));
+        else {
+            if (p0 + p4 + 0 < hw) v.x = __ldg(sp + 0);
+            if (p0 + p4 + 1 < hw) v.y = __ldg(sp + 1);
+            if (p0 + p4 + 2 < hw) v.z = __ldg(sp + 2);
+            if (p0 + p4 + 3 < hw) v.w = __ldg(sp + 3);
+        }
+        tile[c][p4 + 0] = v.x; tile[c][p4 + 1] = v.y; tile[c][p4 + 2] = v.z; tile[c][p4 + 3] = v.w;
     }
     __syncthreads();
-    const int c = c0 + tx;
-    const float ce = cams_embeds ? cams_embeds[cam * C + c] : 0.f;
-    const float le = level_embed[c];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int p = p0 + ty + i * 8;
-        if (p < hw) {
-            float v = tile[tx][ty + i * 8];
-            if (cams_embeds) v = v + ce;
-            v = v + le;
-            tokens[((int64_t)cam * Nv + start + p) * C + c] = from_f32<T>(v);
+    for (int i = 0; i < 2; ++i) {                              // 64 pixels x 8 channel-octets = 512 stores, 2 per thread
+        const int idx = tid + i * 256;
+        const int p = idx >> 3, c8 = (idx & 7) * 8;
+        if (p0 + p < hw) {
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float x = tile[c8 + k][p];
+                if (cams_embeds) x = x + cams_embeds[cam * C + c0 + c8 + k];
+                v[k] = x + level_embed[c0 + c8 + k];
+            }
+            store8(tokens + ((int64_t)cam * Nv + start + p0 + p) * C + c0 + c8, v);
         }
     }
 }
@@ -80,15 +94,28 @@ layernorm256_kernel(const float* __restrict__ x, const float* __restrict__ gamma
     }
 }
 
+// "T32" layout of a [rows, 256] fp32 matrix used for the residual stream on the tensor-core path: 32x32 blocks,
+// inside a block [piece j = (col%32)/4][row%32][4 floats].  A thread that owns one ROW of a tile (the shape
+// tcgen05.ld produces) then reads / writes 16 bytes per instruction with the 32 lanes of a warp contiguous.
+__device__ __forceinline__ int64_t t32_index(int64_t row, int col)
+{
+    return ((((row >> 5) * 8 + (col >> 5)) * 8 + ((col & 31) >> 2)) * 32 + (row & 31)) * 4 + (col & 3);
+}
+
 template <typename T>
 __global__ void prepare_query_kernel(const float* __restrict__ q, const float* __restrict__ pos, int64_t n8,
-                                     float* __restrict__ q_f32, T* __restrict__ q_t, T* __restrict__ q_pos_t)
+                                     float* __restrict__ q_f32, T* __restrict__ q_t, T* __restrict__ q_pos_t, int tiled)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n8) return;
     float v[8], p[8];
     load8(q + i * 8, v);
     load8(pos + i * 8, p);
+    if (q_f32 && tiled) {
+        const int64_t row = (i * 8) >> 8; const int col = (int)((i * 8) & 255);
+        *reinterpret_cast<float4*>(q_f32 + t32_index(row, col)) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(q_f32 + t32_index(row, col + 4)) = make_float4(v[4], v[5], v[6], v[7]);
+    } else
     if (q_f32) store8(q_f32 + i * 8, v);
     if (q_t) store8(q_t + i * 8, v);
 #pragma unroll
@@ -108,6 +135,17 @@ __global__ void bev_pos_kernel(const float* __restrict__ row_embed, const float*
     pos[i] = (c < half) ? col_embed[x * half + c] : row_embed[y * half + (c - half)];
 }
 
+// row-major [rows,256] <-> T32 (dir 0: tile, 1: untile); one thread per 4 floats
+__global__ void t32_convert_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t rows, int dir)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * 64) return;
+    const int64_t row = i >> 6; const int col = (int)(i & 63) * 4;
+    const int64_t a = row * 256 + col, b = t32_index(row, col);
+    if (dir == 0) *reinterpret_cast<float4*>(dst + b) = __ldg(reinterpret_cast<const float4*>(src + a));
+    else          *reinterpret_cast<float4*>(dst + a) = __ldg(reinterpret_cast<const float4*>(src + b));
+}
+
 template <typename T>
 __global__ void cast_kernel(const float* __restrict__ s, T* __restrict__ d, int64_t n)
 {
@@ -121,9 +159,9 @@ template <typename T>
 int launch_pack_level(const float* feat, const float* cams_embeds, const float* level_embed, int num_cams, int C,
                       int hw, int Nv, int start, T* tokens, cudaStream_t stream)
 {
-    OCC_CHECK(C % 32 == 0, "pack_level: C must be a multiple of 32");
-    dim3 grid(ceil_div(hw, 32), C / 32, num_cams), block(32, 8);
-    pack_level_kernel<T><<<grid, block, 0, stream>>>(feat, cams_embeds, level_embed, C, hw, Nv, start, tokens);
+    OCC_CHECK(C % 64 == 0, "pack_level: C must be a multiple of 64");
+    dim3 grid(ceil_div(hw, 64), C / 64, num_cams);
+    pack_level_kernel<T><<<grid, 256, 0, stream>>>(feat, cams_embeds, level_embed, C, hw, Nv, start, tokens);
     OCC_CUDA(cudaGetLastError());
     return 0;
 }
@@ -148,21 +186,28 @@ template int launch_layernorm<bf16>(const float*, const float*, const float*, co
 
 template <typename T>
 int launch_prepare_query(const float* bev_queries, const float* pos, int64_t n, float* q_f32, T* q_t, T* q_pos_t,
-                         cudaStream_t stream)
+                         int tiled, cudaStream_t stream)
 {
     OCC_CHECK(n % 8 == 0, "prepare_query: size must be a multiple of 8");
-    prepare_query_kernel<T><<<ceil_div(n / 8, 256), 256, 0, stream>>>(bev_queries, pos, n / 8, q_f32, q_t, q_pos_t);
+    prepare_query_kernel<T><<<ceil_div(n / 8, 256), 256, 0, stream>>>(bev_queries, pos, n / 8, q_f32, q_t, q_pos_t, tiled);
     OCC_CUDA(cudaGetLastError());
     return 0;
 }
-template int launch_prepare_query<float>(const float*, const float*, int64_t, float*, float*, float*, cudaStream_t);
-template int launch_prepare_query<bf16>(const float*, const float*, int64_t, float*, bf16*, bf16*, cudaStream_t);
+template int launch_prepare_query<float>(const float*, const float*, int64_t, float*, float*, float*, int, cudaStream_t);
+template int launch_prepare_query<bf16>(const float*, const float*, int64_t, float*, bf16*, bf16*, int, cudaStream_t);
 
 int launch_bev_pos(const float* row_embed, const float* col_embed, int bev_h, int bev_w, int half, float* pos,
                    cudaStream_t stream)
 {
     const int64_t n = (int64_t)bev_h * bev_w * 2 * half;
     bev_pos_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(row_embed, col_embed, bev_h, bev_w, half, pos);
+    OCC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_t32_convert(const float* src, float* dst, int64_t rows, int untile, cudaStream_t stream)
+{
+    t32_convert_kernel<<<ceil_div(rows * 64, 256), 256, 0, stream>>>(src, dst, rows, untile);
     OCC_CUDA(cudaGetLastError());
     return 0;
 }

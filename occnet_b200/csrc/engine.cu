@@ -64,7 +64,7 @@ struct occb200_engine {
     bool cameras_set = false, finalized = false, taps = false;
     std::map<std::string, std::vector<float>> host_params;
     std::vector<LayerW> layers;
-    DevBuf bev_queries, pos, cams_embeds, level_embeds;
+    DevBuf bev_queries, pos, pos_t32, cams_embeds, level_embeds;
     DevBuf conv_w[2], conv_b[2], conv_wh[2];
     DevBuf sca_v_all_wh, sca_v_all_b, sca_value_all;     // value_proj of every layer, concatenated (tensor-core path)
     DevBuf hw1, hb1, hw2, hb2, fw1, fb1, fw2, fb2, head_w1h, head_w2h, head_b1c, head_b2c;
@@ -189,9 +189,13 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
     T* q_t = e->q_t.as<T>();
     T* q_pos_t = e->q_pos_t.as<T>();
     const float* pos = e->pos.as<float>();
+    // tensor-core path: LayerNorm is fused into the GEMM epilogues and the fp32 residual stream lives in the T32 layout
+    const bool fuse_ln = sizeof(T) == 2 && c.use_tensor_cores && !e->taps && e->pos_t32.p != nullptr &&
+                         e->layers[0].tsa_o_wh.p != nullptr;
     {
         ProfScope ps(e, st, CAT_PACK);
-        if (launch_prepare_query<T>(e->bev_queries.as<float>(), pos, (int64_t)Nq * C, q_f32, q_t, q_pos_t, st)) return 2;
+        if (launch_prepare_query<T>(e->bev_queries.as<float>(), pos, (int64_t)Nq * C, q_f32, q_t, q_pos_t, fuse_ln ? 1 : 0,
+                                    st)) return 2;
     }
     e->launches++;
     const bool has_prev = prev_bev != nullptr;
@@ -231,7 +235,6 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
             if (launch_tsa_fused<T>(v_prev, v_cur, qproj, c.bev_h, c.bev_w, attn_out, st)) return 2;
         }
         e->launches++;
-        const bool fuse_ln = sizeof(T) == 2 && c.use_tensor_cores && !e->taps && w.tsa_o_wh.p != nullptr;
         if (fuse_ln) {
             if (gemm_ln_fused(e, (const bf16*)attn_out, w.tsa_o_wh.p, w.tsa_o_b.as<float>(), q_f32, w.ln_g[0].as<float>(),
                               w.ln_b[0].as<float>(), nullptr, x_f32, (bf16*)q_t, nullptr, Nq, C, st)) return 2;
@@ -285,7 +288,8 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
                        e->ffn_h.as<T>(), Nq, c.ffn_dim, C, ACT_RELU, st)) return 2;
         if (fuse_ln) {
             if (gemm_ln_fused(e, e->ffn_h.as<bf16>(), w.ffn2_wh.p, w.ffn2_b.as<float>(), q_f32, w.ln_g[2].as<float>(),
-                              w.ln_b[2].as<float>(), pos, x_f32, (bf16*)q_t, (bf16*)q_pos_t, Nq, c.ffn_dim, st)) return 2;
+                              w.ln_b[2].as<float>(), e->pos_t32.as<float>(), x_f32, (bf16*)q_t, (bf16*)q_pos_t, Nq, c.ffn_dim, st))
+                return 2;
             std::swap(q_f32, x_f32);
         } else {
             if (gemm<T, float>(e, e->ffn_h.as<T>(), nullptr, 0, w.ffn2_w.as<float>(), w.ffn2_wh.p, w.ffn2_b.as<float>(),
@@ -300,6 +304,12 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
         if (e->taps)
             OCC_CUDA(cudaMemcpyAsync(e->tap_layer.as<float>() + (size_t)l * Nq * C, q_f32, (size_t)Nq * C * 4,
                                      cudaMemcpyDeviceToDevice, st));
+    }
+    if (fuse_ln) {                                                 // back to row-major for the outputs / voxel decoder
+        ProfScope ps(e, st, CAT_PACK);
+        if (launch_t32_convert(q_f32, x_f32, Nq, 1, st)) return 2;
+        std::swap(q_f32, x_f32);
+        e->launches++;
     }
     if (bev_embed)
         OCC_CUDA(cudaMemcpyAsync(bev_embed, q_f32, (size_t)Nq * C * 4, cudaMemcpyDeviceToDevice, st));
@@ -406,7 +416,7 @@ void occb200_engine_destroy(occb200_engine* e)
                          &w.tsa_q_wh, &w.tsa_o_wh, &w.sca_q_wh, &w.sca_v_wh, &w.sca_o_wh, &w.ffn1_wh, &w.ffn2_wh};
         for (DevBuf* b : all) b->release();
     }
-    DevBuf* all[] = {&e->bev_queries, &e->pos, &e->cams_embeds, &e->level_embeds, &e->conv_w[0], &e->conv_w[1],
+    DevBuf* all[] = {&e->bev_queries, &e->pos, &e->pos_t32, &e->cams_embeds, &e->level_embeds, &e->conv_w[0], &e->conv_w[1],
                      &e->conv_b[0], &e->conv_b[1], &e->conv_wh[0], &e->conv_wh[1], &e->sca_v_all_wh, &e->sca_v_all_b, &e->sca_value_all, &e->hw1, &e->hb1, &e->hw2, &e->hb2,
                      &e->fw1, &e->fb1, &e->fw2, &e->fb2, &e->head_w1h, &e->head_w2h, &e->head_b1c, &e->head_b2c, &e->tokens, &e->sca_value, &e->q_f32, &e->q_t,
                      &e->q_pos_t, &e->q0_t, &e->prev_t, &e->tsa_value, &e->tsa_value_prev, &e->qproj, &e->attn_out,
@@ -454,6 +464,12 @@ int occb200_engine_finalize(occb200_engine* e)
         if (upload(dre, re->data(), re->size()) || upload(dce, ce->data(), ce->size())) return 2;
         if (e->pos.alloc((size_t)Nq * C * 4)) return 2;
         if (launch_bev_pos(dre.as<float>(), dce.as<float>(), c.bev_h, c.bev_w, C / 2, e->pos.as<float>(), 0)) return 2;
+        if (tc) {                                                  // T32 copy of pos for the fused LayerNorm epilogue
+            const size_t rows_pad = ((size_t)Nq + 127) / 128 * 128;
+            if (e->pos_t32.alloc(rows_pad * C * 4)) return 2;
+            OCC_CUDA(cudaMemset(e->pos_t32.p, 0, rows_pad * C * 4));
+            if (launch_t32_convert(e->pos.as<float>(), e->pos_t32.as<float>(), Nq, 0, 0)) return 2;
+        }
         OCC_CUDA(cudaDeviceSynchronize());
         dre.release(); dce.release();
         GETP(le, "transformer.level_embeds", (size_t)c.num_levels * C);
@@ -580,13 +596,16 @@ int occb200_engine_finalize(occb200_engine* e)
     const size_t nvox = (size_t)c.bev_w * c.bev_h * c.pillar_h;
     const size_t ntok = (size_t)c.num_cams * e->Nv;
     int maxq = 8 * c.num_levels * c.sca_points * 3;
-    if (e->tokens.alloc(ntok * C * es) || e->sca_value.alloc(ntok * C * es) || e->q_f32.alloc((size_t)Nq * C * 4) ||
+    const size_t nq_pad = ((size_t)Nq + 127) / 128 * 128;
+    if (e->tokens.alloc(ntok * C * es) || e->sca_value.alloc(ntok * C * es) || e->q_f32.alloc(nq_pad * C * 4) ||
         e->q_t.alloc((size_t)Nq * C * es) || e->q_pos_t.alloc((size_t)Nq * C * es) || e->q0_t.alloc((size_t)Nq * C * es) ||
         e->prev_t.alloc((size_t)Nq * C * es) || e->tsa_value.alloc((size_t)Nq * C * es) ||
         e->tsa_value_prev.alloc((size_t)Nq * C * es) || e->qproj.alloc((size_t)Nq * maxq * 4) ||
-        e->attn_out.alloc((size_t)Nq * C * es) || e->x_f32.alloc((size_t)Nq * C * 4) ||
+        e->attn_out.alloc((size_t)Nq * C * es) || e->x_f32.alloc(nq_pad * C * 4) ||
         e->ffn_h.alloc((size_t)Nq * F * es) || e->vox0.alloc(nvox * mid * es) || e->vox1.alloc(nvox * od * es) ||
         e->vox2.alloc(nvox * od * es) || e->hits.alloc(Nq)) return 2;
+    OCC_CUDA(cudaMemset(e->q_f32.p, 0, nq_pad * C * 4));
+    OCC_CUDA(cudaMemset(e->x_f32.p, 0, nq_pad * C * 4));
     e->host_params.clear();
     e->finalized = true;
     return 0;

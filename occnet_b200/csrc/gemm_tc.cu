@@ -73,7 +73,7 @@ struct LnArgs {                                           // fused LayerNorm epi
 // w_resident: all nk weight k-blocks of this CTA's n-block stay in shared memory for the CTA's lifetime and the
 // ring only carries A tiles; otherwise each stage carries an A tile and a W k-block (v1 behaviour).
 template <typename TC, bool LN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, 1)          // 10 warps -> 3 on one SMSP -> <= 168 regs (16K per SMSP)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmW, const float* __restrict__ bias,
                const float* __restrict__ residual, TC* __restrict__ C, LnArgs ln, int M, int N, int BN, int nk,
@@ -89,6 +89,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     };
     if (threadIdx.x == 0) stamp(0);
+    // Programmatic dependent launch: let the next kernel in the stream start its prologue while this grid drains,
+    // and (below) only wait for the PREVIOUS grid right before touching data it produced.  Weights, barrier and
+    // TMEM setup do not depend on the predecessor.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t w_tile_bytes = BN * BLOCK_K * 2;
@@ -132,6 +136,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tc::tma_load_2d(smem_base + kb * w_tile_bytes, &tmW, w_bar, kb * BLOCK_K, n_blk * BN);
             }
             int s = 0; uint32_t ph = 0;
+            asm volatile("griddepcontrol.wait;" ::: "memory");    // A (and residual) come from the previous kernel
             for (int m_blk = m_first; m_blk < m_tiles; m_blk += m_step) {
                 for (int kb = 0; kb < nk; ++kb) {
                     tc::mbar_wait(empty_bar(s), ph ^ 1);
@@ -187,18 +192,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t stg = bar_base + 256 + 2048 + ew * 4096;  // this warp's staging block (shared address)
         float2* part = reinterpret_cast<float2*>(smem_raw + (bar_base + 256 - tc::smem_u32(smem_raw)));   // [2][128]
         const int crow = lane >> 3, cpiece = lane & 7;           // coalesced shape: row 4*i + crow, 16-byte piece cpiece
-        auto sts4 = [&](int r, int piece, float4 v) {
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + r * 128 + ((piece ^ (r & 7)) << 4)),
-                         "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-        };
-        auto lds4 = [&](int r, int piece) {
-            float4 v;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                         : "r"(stg + r * 128 + ((piece ^ (r & 7)) << 4)) : "memory");
-            return v;
-        };
+        // plain C++ accesses through a generic pointer (not volatile asm) so the compiler may overlap the
+        // shared-memory round trip with the global stores of the previous rows
+        float4* const stg4 = reinterpret_cast<float4*>(smem_raw + (stg - tc::smem_u32(smem_raw)));
+        auto sts4 = [&](int r, int piece, float4 v) { stg4[r * 8 + (piece ^ (r & 7))] = v; };
+        auto lds4 = [&](int r, int piece) { return stg4[r * 8 + (piece ^ (r & 7))]; };
         int as = 0; uint32_t aph = 0;
         int etile = 0;
+        asm volatile("griddepcontrol.wait;" ::: "memory");        // before the first global read / write of this role
         for (int m_blk = m_first; m_blk < m_tiles; m_blk += m_step) {
             const int row0 = m_blk * BLOCK_M + quarter * 32;     // first row of this warp's 32-row block
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * 256;
@@ -224,26 +225,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 __syncwarp();
             };
-            fetch(residual, N, n_blk * BN + cbeg);               // independent of the MMA: issue before waiting on it
-            tc::mbar_wait(tfull_bar(as), aph);
-            if (warp == 2 && lane == 0 && etile < 3) stamp(4 + etile * 3);          // accumulator ready
-            tc::tc_fence_after();
+            if constexpr (!LN) {
+                fetch(residual, N, n_blk * BN + cbeg);           // independent of the MMA: issue before waiting on it
+                tc::mbar_wait(tfull_bar(as), aph);
+                if (warp == 2 && lane == 0 && etile < 3) stamp(4 + etile * 3);      // accumulator ready
+                tc::tc_fence_after();
+            }
             if constexpr (LN) {
+                // Residual stream (residual, y_f32) and pos live in the T32 block layout: the thread that owns row
+                // `lane` of this warp's 32-row block reads / writes piece j of chunk cb at
+                // ((R*8 + cb)*8 + j)*32 + lane  (float4 units) -- 512 contiguous bytes per warp instruction, no
+                // shared-memory transpose.  Only the row-major bf16 operand copies go through the staging block.
+                const size_t blk4 = (size_t)(row0 >> 5) * 8 * 8 * 32 + lane;          // float4 index of (R, cb=0, j=0, lane)
+                auto t32_load = [&](const float* base, int c0, float4 (&dst)[8]) {
+                    const float4* p4 = reinterpret_cast<const float4*>(base) + blk4 + (size_t)(c0 >> 5) * 256;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dst[j] = __ldg(p4 + j * 32);
+                };
                 float sum = 0.f, sumsq = 0.f;
+                float4 nxt[8];
+                t32_load(residual, cbeg, nxt);
+                tc::mbar_wait(tfull_bar(as), aph);
+                if (warp == 2 && lane == 0 && etile < 3) stamp(4 + etile * 3);          // accumulator ready
+                tc::tc_fence_after();
 #pragma unroll
                 for (int ci = 0; ci < 4; ++ci) {                 // 128 columns = 4 chunks per warp
                     const int c0 = cbeg + ci * 32;
-                    float q[32];
-                    to_rows(q);                                  // residual of my row, this chunk
-                    if (ci + 1 < 4) fetch(residual, 256, c0 + 32);
+                    float4 q[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) q[j] = nxt[j];
+                    if (ci + 1 < 4) t32_load(residual, c0 + 32, nxt);
                     uint32_t r[32];
                     tc::tmem_ld32(taddr + c0, r);
                     tc::tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0) + i);
-                        const float x0 = __uint_as_float(r[4 * i]) + b.x + q[4 * i], x1 = __uint_as_float(r[4 * i + 1]) + b.y + q[4 * i + 1];
-                        const float x2 = __uint_as_float(r[4 * i + 2]) + b.z + q[4 * i + 2], x3 = __uint_as_float(r[4 * i + 3]) + b.w + q[4 * i + 3];
+                        const float x0 = __uint_as_float(r[4 * i]) + b.x + q[i].x, x1 = __uint_as_float(r[4 * i + 1]) + b.y + q[i].y;
+                        const float x2 = __uint_as_float(r[4 * i + 2]) + b.z + q[i].z, x3 = __uint_as_float(r[4 * i + 3]) + b.w + q[i].w;
                         sum += (x0 + x1) + (x2 + x3);
                         sumsq = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, fmaf(x3, x3, sumsq))));
                         r[4 * i] = __float_as_uint(x0); r[4 * i + 1] = __float_as_uint(x1);
@@ -251,7 +270,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     tc::tmem_st32(taddr + c0, r);
                 }
-                if (ln.y_pos_bf16) fetch(ln.pos, 256, cbeg);
+                if (ln.y_pos_bf16) t32_load(ln.pos, cbeg, nxt);
                 // exchange the half-row statistics with the warp that owns the other 128 columns of these rows
                 part[half * 128 + quarter * 32 + lane] = make_float2(sum, sumsq);
                 tc::tmem_st_wait();
@@ -266,8 +285,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     uint32_t r[32];
                     tc::tmem_ld32(taddr + c0, r);
                     tc::tmem_ld_wait();
+                    float4* yo = reinterpret_cast<float4*>(ln.y_f32) + blk4 + (size_t)(c0 >> 5) * 256;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {                // normalise my row, stage it
+                    for (int j = 0; j < 8; ++j) {                // normalise my row: fp32 straight to T32, bf16 via staging
                         const float4 g = __ldg(reinterpret_cast<const float4*>(ln.gamma + c0) + j);
                         const float4 be = __ldg(reinterpret_cast<const float4*>(ln.beta + c0) + j);
                         float4 y;
@@ -275,27 +295,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         y.y = (__uint_as_float(r[4 * j + 1]) - mean) * rstd * g.y + be.y;
                         y.z = (__uint_as_float(r[4 * j + 2]) - mean) * rstd * g.z + be.z;
                         y.w = (__uint_as_float(r[4 * j + 3]) - mean) * rstd * g.w + be.w;
-                        sts4(lane, j, y);
+                        if (ln.y_f32) yo[j * 32] = y;
+                        // staging block: bytes [0,2K) = y as bf16 rows of 64 B, [2K,4K) = (y + pos) as bf16
+                        reinterpret_cast<uint2*>(stg4)[lane * 8 + (j ^ (lane & 7))] =
+                            make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+                        if (ln.y_pos_bf16) {
+                            const float4 p4 = nxt[j];
+                            reinterpret_cast<uint2*>(stg4)[256 + lane * 8 + (j ^ (lane & 7))] =
+                                make_uint2(pack_bf16x2(y.x + p4.x, y.y + p4.y), pack_bf16x2(y.z + p4.z, y.w + p4.w));
+                        }
                     }
                     __syncwarp();
+                    if (ln.y_pos_bf16 && ci + 1 < 4) t32_load(ln.pos, c0 + 32, nxt);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {                // coalesced stores: 4 rows x 128 B per instruction
-                        const int rr = 4 * i + crow, grow = row0 + rr;
-                        const float4 y = lds4(rr, cpiece);
+                    for (int i = 0; i < 4; ++i) {                // coalesced bf16 stores: 8 rows x 64 B per instruction
+                        const int rr = 8 * i + (lane >> 2), grow = row0 + rr, pc = lane & 3;   // 16-byte piece pc = cols 8pc..8pc+7
                         if (grow < M) {
-                            const size_t o = (size_t)grow * 256 + c0 + cpiece * 4;
-                            if (ln.y_f32) *reinterpret_cast<float4*>(ln.y_f32 + o) = y;
-                            if (ln.y_bf16)
-                                *reinterpret_cast<uint2*>(ln.y_bf16 + o) = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+                            const size_t o = (size_t)grow * 256 + c0 + pc * 8;
+                            const uint2 a = reinterpret_cast<uint2*>(stg4)[rr * 8 + ((2 * pc) ^ (rr & 7))];
+                            const uint2 b = reinterpret_cast<uint2*>(stg4)[rr * 8 + ((2 * pc + 1) ^ (rr & 7))];
+                            if (ln.y_bf16) *reinterpret_cast<uint4*>(ln.y_bf16 + o) = make_uint4(a.x, a.y, b.x, b.y);
                             if (ln.y_pos_bf16) {
-                                const float4 p4 = pre[i];
-                                *reinterpret_cast<uint2*>(ln.y_pos_bf16 + o) =
-                                    make_uint2(pack_bf16x2(y.x + p4.x, y.y + p4.y), pack_bf16x2(y.z + p4.z, y.w + p4.w));
+                                const uint2 c = reinterpret_cast<uint2*>(stg4)[256 + rr * 8 + ((2 * pc) ^ (rr & 7))];
+                                const uint2 d = reinterpret_cast<uint2*>(stg4)[256 + rr * 8 + ((2 * pc + 1) ^ (rr & 7))];
+                                *reinterpret_cast<uint4*>(ln.y_pos_bf16 + o) = make_uint4(c.x, c.y, d.x, d.y);
                             }
                         }
                     }
                     __syncwarp();
-                    if (ln.y_pos_bf16 && ci + 1 < 4) fetch(ln.pos, 256, c0 + 32);
                 }
             } else {
                 const int nchunk = ncol >> 5;                    // BN/2 is a multiple of 32 for every plan (<= 4 chunks)
@@ -437,10 +464,19 @@ int launch(const bf16* A, const bf16* A2, int K1, const bf16* W, const float* bi
         OCC_CUDA(cudaMalloc(&dbg, (size_t)grid * 16 * sizeof(long long)));
         OCC_CUDA(cudaMemsetAsync(dbg, 0, (size_t)grid * 16 * sizeof(long long), stream));
     }
-    gemm_tc_kernel<TC, LN><<<grid, NUM_THREADS, p.smem, stream>>>(tmA, tmA2, tmW, bias, residual, C, ln, M, N, p.BN,
-                                                                 K / BLOCK_K, K1 / BLOCK_K, act, p.resident, p.stages,
-                                                                 blocked_out ? (long long)p.BN : (long long)N,
-                                                                 blocked_out ? (long long)M * p.BN : (long long)p.BN, dbg);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = p.smem; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        const int nk = K / BLOCK_K, nk1 = K1 / BLOCK_K, res = p.resident, stg = p.stages;
+        const long long ldc = blocked_out ? (long long)p.BN : (long long)N;
+        const long long nbs = blocked_out ? (long long)M * p.BN : (long long)p.BN;
+        OCC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<TC, LN>, tmA, tmA2, tmW, bias, residual, C, ln, M, N, p.BN, nk, nk1,
+                                    act, res, stg, ldc, nbs, dbg));
+    }
     OCC_CUDA(cudaGetLastError());
     if (want_dbg) {                                               // development aid: per-CTA timeline in ns
         std::vector<long long> h((size_t)grid * 16);
@@ -483,6 +519,7 @@ int gemm_tc_blocked256(const bf16* A, const bf16* W, const float* bias, bf16* C,
     return launch<bf16, false>(A, nullptr, 0, W, bias, nullptr, C, LnArgs{}, M, N, K, ACT_NONE, stream, true);
 }
 
+// residual, y_f32 and pos are in the T32 block layout (elementwise.cu), rows padded to a multiple of 32
 int gemm_tc_ln(const bf16* A, const bf16* W, const float* bias, const float* residual, const float* gamma,
                const float* beta, const float* pos, float* y_f32, bf16* y_bf16, bf16* y_pos_bf16, int M, int K,
                cudaStream_t stream)

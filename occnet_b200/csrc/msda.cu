@@ -105,6 +105,84 @@ __device__ __forceinline__ void gather_sample(const T* __restrict__ base, int W,
     }
 }
 
+// ---- bf16 value path: Blackwell's mixed-precision FMA (PTX fma.rn.f32.bf16 -> SASS FHFMA.BF16) multiplies two bf16
+// operands exactly and accumulates in fp32, and it can read either 16-bit half of a register: the bf16 -> fp32
+// unpack disappears.  The four corner weights travel as two packed bf16 pairs (3 shuffles per sample, not 5).
+__device__ __forceinline__ float fhfma_lo(float acc, uint32_t v, uint32_t w_lo16)
+{
+    const unsigned short a = (unsigned short)(v & 0xffffu), b = (unsigned short)(w_lo16 & 0xffffu);
+    asm("fma.rn.f32.bf16 %0, %1, %2, %0;" : "+f"(acc) : "h"(a), "h"(b));
+    return acc;
+}
+__device__ __forceinline__ float fhfma_hi(float acc, uint32_t v, uint32_t w_lo16)
+{
+    const unsigned short a = (unsigned short)(v >> 16), b = (unsigned short)(w_lo16 & 0xffffu);
+    asm("fma.rn.f32.bf16 %0, %1, %2, %0;" : "+f"(acc) : "h"(a), "h"(b));
+    return acc;
+}
+__device__ __forceinline__ void fma_word4(float (&acc)[8], const uint4& v, uint32_t w)
+{
+    acc[0] = fhfma_lo(acc[0], v.x, w); acc[1] = fhfma_hi(acc[1], v.x, w);
+    acc[2] = fhfma_lo(acc[2], v.y, w); acc[3] = fhfma_hi(acc[3], v.y, w);
+    acc[4] = fhfma_lo(acc[4], v.z, w); acc[5] = fhfma_hi(acc[5], v.z, w);
+    acc[6] = fhfma_lo(acc[6], v.w, w); acc[7] = fhfma_hi(acc[7], v.w, w);
+}
+// accumulator abstraction: bf16 values -> float[8] + FHFMA; fp32 values -> float2[4] + FFMA2
+template <typename T> struct Acc;
+template <> struct Acc<bf16> {
+    float a[8];
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = 0.f;
+    }
+    __device__ __forceinline__ void gather(const bf16* __restrict__ base, int W, int code, uint32_t w12, uint32_t w34) {
+        if (!(code & CODE_VALID)) return;
+        const bf16* p = base + (int64_t)(code & CODE_OFF_MASK) * 256;
+        const int dw = (code & CODE_DW) ? 256 : 0, dh = (code & CODE_DH) ? W * 256 : 0;
+        const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(p)), v2 = __ldg(reinterpret_cast<const uint4*>(p + dw));
+        const uint4 v3 = __ldg(reinterpret_cast<const uint4*>(p + dh)), v4 = __ldg(reinterpret_cast<const uint4*>(p + dh + dw));
+        fma_word4(a, v1, w12); fma_word4(a, v2, w12 >> 16); fma_word4(a, v3, w34); fma_word4(a, v4, w34 >> 16);
+    }
+    __device__ __forceinline__ void finish(float (&o)[8], float scale, bool divide) const {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = divide ? __fdiv_rn(a[i], scale) : a[i] * scale;
+    }
+};
+template <> struct Acc<float> {
+    float2 a[4];
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = make_float2(0.f, 0.f);
+    }
+    __device__ __forceinline__ void gather(const float* __restrict__ base, int W, int code, uint32_t w12, uint32_t w34,
+                                           float c1, float c2, float c3, float c4) {
+        gather_sample<float>(base, W, code, c1, c2, c3, c4, a);
+    }
+    __device__ __forceinline__ void finish(float (&o)[8], float scale, bool divide) const {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            o[2 * i] = divide ? __fdiv_rn(a[i].x, scale) : a[i].x * scale;
+            o[2 * i + 1] = divide ? __fdiv_rn(a[i].y, scale) : a[i].y * scale;
+        }
+    }
+};
+// one sample: broadcast the owner lane's prepared descriptor to the 4 lanes of the head and gather
+template <typename T>
+__device__ __forceinline__ void shuffle_gather(Acc<T>& acc, const T* __restrict__ base, int W, const SamplePrep& sm, int src)
+{
+    const unsigned FULLM = 0xffffffffu;
+    const int code = __shfl_sync(FULLM, sm.code, src);
+    if constexpr (sizeof(T) == 2) {
+        const uint32_t w12 = __shfl_sync(FULLM, pack_bf16x2(sm.c1, sm.c2), src);
+        const uint32_t w34 = __shfl_sync(FULLM, pack_bf16x2(sm.c3, sm.c4), src);
+        acc.gather(base, W, code, w12, w34);
+    } else {
+        const float c1 = __shfl_sync(FULLM, sm.c1, src), c2 = __shfl_sync(FULLM, sm.c2, src);
+        const float c3 = __shfl_sync(FULLM, sm.c3, src), c4 = __shfl_sync(FULLM, sm.c4, src);
+        acc.gather(base, W, code, 0u, 0u, c1, c2, c3, c4);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Operator boundary: value [B,Nv,M,C] f32, loc [B,Nq,M,L,P,2] (x,y), w [B,Nq,M,L,P] -> [B,Nq,M*C]
 // One thread per (b, q, head, 8-channel slice) when C % 8 == 0, otherwise per channel.
@@ -194,30 +272,18 @@ tsa_fused_kernel(const T* __restrict__ value_prev, const T* __restrict__ value_c
 
     const SamplePrep sa = prep_sample(him0, wim0, wt0, bev_h, bev_w);
     const SamplePrep sb = prep_sample(him1, wim1, wt1, bev_h, bev_w);
-    float2 acc2[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) acc2[i] = make_float2(0.f, 0.f);
+    Acc<T> accu;
+    accu.zero();
     const int grp = lane & ~3;
 #pragma unroll
     for (int o = 0; o < 4; ++o) {                            // owner sub-lane o holds samples (o>>1, (o&1)*2 + {0,1})
         const int src = grp | o;
         const T* base = ((o >> 1) == 0 ? value_prev : value_cur) + head * 32 + s * 8;
-        {
-            const int code = __shfl_sync(0xffffffffu, sa.code, src);
-            const float c1 = __shfl_sync(0xffffffffu, sa.c1, src), c2 = __shfl_sync(0xffffffffu, sa.c2, src);
-            const float c3 = __shfl_sync(0xffffffffu, sa.c3, src), c4 = __shfl_sync(0xffffffffu, sa.c4, src);
-            gather_sample<T>(base, bev_w, code, c1, c2, c3, c4, acc2);
-        }
-        {
-            const int code = __shfl_sync(0xffffffffu, sb.code, src);
-            const float c1 = __shfl_sync(0xffffffffu, sb.c1, src), c2 = __shfl_sync(0xffffffffu, sb.c2, src);
-            const float c3 = __shfl_sync(0xffffffffu, sb.c3, src), c4 = __shfl_sync(0xffffffffu, sb.c4, src);
-            gather_sample<T>(base, bev_w, code, c1, c2, c3, c4, acc2);
-        }
+        shuffle_gather<T>(accu, base, bev_w, sa, src);
+        shuffle_gather<T>(accu, base, bev_w, sb, src);
     }
     float acc[8];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { acc[2 * i] = acc2[i].x * 0.5f; acc[2 * i + 1] = acc2[i].y * 0.5f; }
+    accu.finish(acc, 0.5f, false);
     store8(out + (int64_t)q * 256 + head * 32 + s * 8, acc);
 }
 
@@ -289,9 +355,8 @@ sca_fused_kernel(const T* __restrict__ value, const float* __restrict__ qproj, S
     const int count = __popc(vis);
     if (hits && lane == 0) hits[q] = (uint8_t)count;
 
-    float2 acc2[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) acc2[i] = make_float2(0.f, 0.f);
+    Acc<T> accu;
+    accu.zero();
 
     if (count > 0) {
         // ---- owner lane (head, level = s): 8 points x (dx, dy) and 8 logits
@@ -342,22 +407,13 @@ sca_fused_kernel(const T* __restrict__ value, const float* __restrict__ qproj, S
                 const float h_im = __fadd_rn(v, offn[2 * p + 1]) * own_h - 0.5f;
                 const SamplePrep sm = prep_sample(h_im, w_im, wl[p], own_H, own_W);   // my (head, level s, point p)
 #pragma unroll
-                for (int l = 0; l < 4; ++l) {
-                    const int src = grp | l;
-                    const int code = __shfl_sync(FULL, sm.code, src);
-                    const float c1 = __shfl_sync(FULL, sm.c1, src), c2 = __shfl_sync(FULL, sm.c2, src);
-                    const float c3 = __shfl_sync(FULL, sm.c3, src), c4 = __shfl_sync(FULL, sm.c4, src);
-                    gather_sample<T>(vcam + (int64_t)lg.start[l] * 256, lg.w[l], code, c1, c2, c3, c4, acc2);
-                }
+                for (int l = 0; l < 4; ++l)
+                    shuffle_gather<T>(accu, vcam + (int64_t)lg.start[l] * 256, lg.w[l], sm, grp | l);
             }
         }
-        const float cnt = (float)count;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { acc2[i].x = __fdiv_rn(acc2[i].x, cnt); acc2[i].y = __fdiv_rn(acc2[i].y, cnt); }
     }
     float acc[8];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { acc[2 * i] = acc2[i].x; acc[2 * i + 1] = acc2[i].y; }
+    accu.finish(acc, (float)max(count, 1), true);
     store8(out + (int64_t)q * 256 + head * 32 + s * 8, acc);
 }
 
