@@ -108,10 +108,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_slot = bar_base + (2 * MAX_STAGES + 5) * 8;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = N / BN;
-    // CTA -> (fixed n block, strided m tiles) so that a resident weight block serves every tile of the CTA
+    const int n_tiles = N / BN;
+    // CTA -> (fixed n block, contiguous row range): a resident weight block serves every tile of the CTA, and the
+    // rows are dealt out in 32-row blocks so that every CTA gets (almost) the same number of ROWS.  With whole
+    // 128-row tiles, 313 tiles on 148 CTAs meant 3 tile-epilogues for some CTAs and 2 for the rest (70 % balance);
+    // with row ranges the last tile of a CTA is partial and its (memory-bound) epilogue only touches the rows it owns.
     const int n_blk = blockIdx.x % n_tiles;
-    const int m_first = blockIdx.x / n_tiles, m_step = gridDim.x / n_tiles;
+    const int grp = blockIdx.x / n_tiles, ngrp = gridDim.x / n_tiles;
+    const int nb32 = (M + 31) >> 5;
+    const int row_begin = (int)(((long long)nb32 * grp) / ngrp) << 5;
+    const int row_end = min(M, (int)(((long long)nb32 * (grp + 1)) / ngrp) << 5);
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmA); tc::tma_prefetch_desc(&tmA2); tc::tma_prefetch_desc(&tmW);
@@ -137,13 +143,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             int s = 0; uint32_t ph = 0;
             asm volatile("griddepcontrol.wait;" ::: "memory");    // A (and residual) come from the previous kernel
-            for (int m_blk = m_first; m_blk < m_tiles; m_blk += m_step) {
+            for (int m_row = row_begin; m_row < row_end; m_row += BLOCK_M) {
                 for (int kb = 0; kb < nk; ++kb) {
                     tc::mbar_wait(empty_bar(s), ph ^ 1);
                     tc::mbar_arrive_expect_tx(full_bar(s), stage_bytes);
                     const uint32_t a_dst = ring_base + s * stage_bytes;
-                    if (kb < nk1) tc::tma_load_2d(a_dst, &tmA, full_bar(s), kb * BLOCK_K, m_blk * BLOCK_M);
-                    else          tc::tma_load_2d(a_dst, &tmA2, full_bar(s), (kb - nk1) * BLOCK_K, m_blk * BLOCK_M);
+                    if (kb < nk1) tc::tma_load_2d(a_dst, &tmA, full_bar(s), kb * BLOCK_K, m_row);
+                    else          tc::tma_load_2d(a_dst, &tmA2, full_bar(s), (kb - nk1) * BLOCK_K, m_row);
                     if (!w_resident)
                         tc::tma_load_2d(a_dst + A_TILE_BYTES, &tmW, full_bar(s), kb * BLOCK_K, n_blk * BN);
                     if (++s == stages) { s = 0; ph ^= 1; }
@@ -157,7 +163,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (w_resident) { tc::mbar_wait(w_bar, 0); tc::tc_fence_after(); }
             stamp(2);                                            // weights resident
             int tcount = 0;
-            for (int m_blk = m_first; m_blk < m_tiles; m_blk += m_step, ++tcount) {
+            for (int m_row = row_begin; m_row < row_end; m_row += BLOCK_M, ++tcount) {
                 tc::mbar_wait(tempty_bar(as), aph ^ 1);
                 tc::tc_fence_after();
                 for (int kb = 0; kb < nk; ++kb) {
@@ -200,8 +206,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int as = 0; uint32_t aph = 0;
         int etile = 0;
         asm volatile("griddepcontrol.wait;" ::: "memory");        // before the first global read / write of this role
-        for (int m_blk = m_first; m_blk < m_tiles; m_blk += m_step) {
-            const int row0 = m_blk * BLOCK_M + quarter * 32;     // first row of this warp's 32-row block
+        for (int m_row = row_begin; m_row < row_end; m_row += BLOCK_M) {
+            const int row0 = m_row + quarter * 32;               // first row of this warp's 32-row block
+            const int M = row0 < row_end ? row_end : 0;          // rows >= row_end belong to the next CTA: mask them
+            if (M == 0) {                                        // this warp's 32-row block is past the CTA's range
+                tc::mbar_wait(tfull_bar(as), aph);               // (warp-uniform; the partner column-half warp skips too)
+                tc::tc_fence_before();
+                tc::mbar_arrive(tempty_bar(as));
+                ++etile;
+                if (++as == 2) { as = 0; aph ^= 1; }
+                continue;
+            }
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * 256;
             // coalesced fetch of a [32 rows x 32 cols] fp32 block (rows row0.., columns c..c+31) into registers
             float4 pre[8];
@@ -456,7 +471,7 @@ int launch(const bf16* A, const bf16* A2, int K1, const bf16* W, const float* bi
     }
     const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = N / p.BN;
     int per_n = num_sms / n_tiles;
-    if (per_n > m_tiles) per_n = m_tiles;
+    if (per_n > m_tiles) per_n = m_tiles;                        // (row ranges are dealt in 32-row blocks: >= 1 per CTA)
     const int grid = per_n * n_tiles;
     long long* dbg = nullptr;
     static const bool want_dbg = getenv("OCC_GEMM_TIMELINE") != nullptr;

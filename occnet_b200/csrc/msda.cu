@@ -15,6 +15,8 @@
 // a lane accumulates 8 of the head's 32 channels, so one warp-wide 128-bit load instruction
 // fetches 8 independent 64-byte (bf16) corner rows.  Per-sample scalars (location, weight) live
 // in one owner lane per (head, level) and are broadcast inside the 4-lane group with shuffles.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -326,8 +328,8 @@ __global__ void project_pillars_kernel(ScaParams sp, float* __restrict__ ref_cam
 //   value [num_cams, Nv, 8, 32] T;  qproj [Nq, 768] f32 = [offsets (head,level,point,xy) | logits (head, level*point)]
 //   out  [Nq, 256] T  = sum_{visible cams} MSDA_cam(q) / max(1, #visible cams)
 //   hits (optional) [Nq] u8 = #visible cams (for tests / statistics)
-template <typename T>
-__global__ void __launch_bounds__(256, 3)
+template <typename T, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 sca_fused_kernel(const T* __restrict__ value, const float* __restrict__ qproj, ScaParams sp, LevelGeom lg,
                  int Nv, T* __restrict__ out, uint8_t* __restrict__ hits)
 {
@@ -457,7 +459,9 @@ int launch_sca_fused(const T* value, const float* qproj, const ScaParams& sp, co
     OCC_CHECK(lg.num_levels == 4 && sp.num_cams <= 8 && sp.D <= 8 && sp.D >= 1 && 8 % sp.D == 0,
               "sca_fused: supports 4 levels, <= 8 cameras, pillar anchors in {1,2,4,8}");
     const int Nq = sp.bev_h * sp.bev_w;
-    sca_fused_kernel<T><<<ceil_div(Nq, 8), 256, 0, stream>>>(value, qproj, sp, lg, Nv, out, hits);
+    static const int minb = getenv("OCC_SCA_MINB") ? atoi(getenv("OCC_SCA_MINB")) : 3;   // tuning knob (registers vs occupancy)
+    if (minb == 2) sca_fused_kernel<T, 2><<<ceil_div(Nq, 8), 256, 0, stream>>>(value, qproj, sp, lg, Nv, out, hits);
+    else           sca_fused_kernel<T, 3><<<ceil_div(Nq, 8), 256, 0, stream>>>(value, qproj, sp, lg, Nv, out, hits);
     OCC_CUDA(cudaGetLastError());
     return 0;
 }
