@@ -59,8 +59,12 @@ __device__ __forceinline__ void bilinear_acc8(const T* __restrict__ base, int H,
 // packed descriptor (clamped pixel offset + which neighbours exist) and four pre-multiplied corner weights;
 // the four lanes of the head then gather their 8 channels with unconditional, in-bounds 128-bit loads.
 struct SamplePrep { int code; float c1, c2, c3, c4; };
-constexpr int CODE_DW = 1 << 20, CODE_DH = 1 << 21, CODE_VALID = 1 << 22, CODE_OFF_MASK = (1 << 20) - 1;
+constexpr int CODE_VALID = 1 << 30, CODE_OFF_MASK = CODE_VALID - 1;
 
+// The 2x2 block that is fetched always starts at a pixel clamped to [0,H-2] x [0,W-2], so its four addresses are
+// base, base+1 pixel, base+1 row, base+1 row+1 pixel with CONSTANT strides (no per-sample border flags, no branches).
+// The bilinear corner weights are assigned to the positions of that block that coincide with in-bounds true corners
+// (zero padding for the others); for interior samples this is exactly the usual (hh*hw, hh*lw, lh*hw, lh*lw).
 __device__ __forceinline__ SamplePrep prep_sample(float h_im, float w_im, float wt, int H, int W)
 {
     SamplePrep s;
@@ -68,13 +72,14 @@ __device__ __forceinline__ SamplePrep prep_sample(float h_im, float w_im, float 
     const float hf = valid ? floorf(h_im) : 0.f, wf = valid ? floorf(w_im) : 0.f;
     const int h_lo = (int)hf, w_lo = (int)wf;
     const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
-    const bool top = h_lo >= 0, bot = h_lo + 1 <= H - 1, lef = w_lo >= 0, rig = w_lo + 1 <= W - 1;
-    s.c1 = (valid && top && lef) ? wt * (hh * hw) : 0.f;
-    s.c2 = (valid && top && rig) ? wt * (hh * lw) : 0.f;
-    s.c3 = (valid && bot && lef) ? wt * (lh * hw) : 0.f;
-    s.c4 = (valid && bot && rig) ? wt * (lh * lw) : 0.f;
-    const int h0 = max(h_lo, 0), h1 = min(h_lo + 1, H - 1), w0 = max(w_lo, 0), w1 = min(w_lo + 1, W - 1);
-    s.code = (h0 * W + w0) | ((w1 - w0) ? CODE_DW : 0) | ((h1 - h0) ? CODE_DH : 0) | (valid ? CODE_VALID : 0);
+    const int hb = min(max(h_lo, 0), H - 2), wb = min(max(w_lo, 0), W - 2);
+    const float rw0 = (h_lo == hb) ? hh : ((h_lo + 1 == hb) ? lh : 0.f);
+    const float rw1 = (h_lo == hb + 1) ? hh : ((h_lo == hb) ? lh : 0.f);
+    const float cw0 = (w_lo == wb) ? hw : ((w_lo + 1 == wb) ? lw : 0.f);
+    const float cw1 = (w_lo == wb + 1) ? hw : ((w_lo == wb) ? lw : 0.f);
+    const float g = valid ? wt : 0.f;
+    s.c1 = g * (rw0 * cw0); s.c2 = g * (rw0 * cw1); s.c3 = g * (rw1 * cw0); s.c4 = g * (rw1 * cw1);
+    s.code = (hb * W + wb) | (valid ? CODE_VALID : 0);
     return s;
 }
 
@@ -93,11 +98,10 @@ template <typename T>
 __device__ __forceinline__ void gather_sample(const T* __restrict__ base, int W, int code, float c1, float c2, float c3,
                                               float c4, float2 (&acc)[4])
 {
-    if (!(code & CODE_VALID)) return;                            // uniform inside the 4-lane head group
+    if (!(code & CODE_VALID)) return;                            // sample outside the map: contributes nothing
     const T* p = base + (int64_t)(code & CODE_OFF_MASK) * 256;
-    const int dw = (code & CODE_DW) ? 256 : 0, dh = (code & CODE_DH) ? W * 256 : 0;
     float v1[8], v2[8], v3[8], v4[8];
-    load8(p, v1); load8(p + dw, v2); load8(p + dh, v3); load8(p + dh + dw, v4);
+    load8(p, v1); load8(p + 256, v2); load8(p + (int64_t)W * 256, v3); load8(p + (int64_t)W * 256 + 256, v4);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         ffma2(acc[i], v1[2 * i], v1[2 * i + 1], c1);
@@ -138,11 +142,11 @@ template <> struct Acc<bf16> {
         for (int i = 0; i < 8; ++i) a[i] = 0.f;
     }
     __device__ __forceinline__ void gather(const bf16* __restrict__ base, int W, int code, uint32_t w12, uint32_t w34) {
-        if (!(code & CODE_VALID)) return;
+        if (!(code & CODE_VALID)) return;                        // sample outside the map (uniform in the 4-lane group)
         const bf16* p = base + (int64_t)(code & CODE_OFF_MASK) * 256;
-        const int dw = (code & CODE_DW) ? 256 : 0, dh = (code & CODE_DH) ? W * 256 : 0;
-        const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(p)), v2 = __ldg(reinterpret_cast<const uint4*>(p + dw));
-        const uint4 v3 = __ldg(reinterpret_cast<const uint4*>(p + dh)), v4 = __ldg(reinterpret_cast<const uint4*>(p + dh + dw));
+        const bf16* pr = p + (int64_t)W * 256;
+        const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(p)), v2 = __ldg(reinterpret_cast<const uint4*>(p + 256));
+        const uint4 v3 = __ldg(reinterpret_cast<const uint4*>(pr)), v4 = __ldg(reinterpret_cast<const uint4*>(pr + 256));
         fma_word4(a, v1, w12); fma_word4(a, v2, w12 >> 16); fma_word4(a, v3, w34); fma_word4(a, v4, w34 >> 16);
     }
     __device__ __forceinline__ void finish(float (&o)[8], float scale, bool divide) const {
@@ -331,10 +335,14 @@ __global__ void project_pillars_kernel(ScaParams sp, float* __restrict__ ref_cam
 template <typename T, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 sca_fused_kernel(const T* __restrict__ value, const float* __restrict__ qproj, ScaParams sp, LevelGeom lg,
-                 int Nv, T* __restrict__ out, uint8_t* __restrict__ hits)
+                 int Nv, T* __restrict__ out, uint8_t* __restrict__ hits, int tile_mode)
 {
     const int Nq = sp.bev_h * sp.bev_w;
-    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tile_mode) {                                             // CTA = 4 (x) x 2 (y) BEV tile: neighbouring pillars
+        const int tiles_x = sp.bev_w >> 2, w = threadIdx.x >> 5; // project to neighbouring pixels in every camera
+        q = ((blockIdx.x / tiles_x) * 2 + (w >> 2)) * sp.bev_w + (blockIdx.x % tiles_x) * 4 + (w & 3);
+    }
     if (q >= Nq) return;
     const int lane = threadIdx.x & 31, head = lane >> 2, s = lane & 3;   // s doubles as the owned level
     const unsigned FULL = 0xffffffffu;
@@ -444,6 +452,7 @@ template <typename T>
 int launch_tsa_fused(const T* value_prev, const T* value_cur, const float* qproj, int bev_h, int bev_w, T* out,
                      cudaStream_t stream)
 {
+    OCC_CHECK(bev_h >= 2 && bev_w >= 2, "tsa_fused: the BEV grid must be at least 2x2");
     const int Nq = bev_h * bev_w;
     tsa_fused_kernel<T><<<ceil_div(Nq, 8), 256, 0, stream>>>(value_prev, value_cur, qproj, bev_h, bev_w, out);
     OCC_CUDA(cudaGetLastError());
@@ -458,10 +467,13 @@ int launch_sca_fused(const T* value, const float* qproj, const ScaParams& sp, co
 {
     OCC_CHECK(lg.num_levels == 4 && sp.num_cams <= 8 && sp.D <= 8 && sp.D >= 1 && 8 % sp.D == 0,
               "sca_fused: supports 4 levels, <= 8 cameras, pillar anchors in {1,2,4,8}");
+    for (int l = 0; l < 4; ++l) OCC_CHECK(lg.h[l] >= 2 && lg.w[l] >= 2, "sca_fused: every level must be at least 2x2");
     const int Nq = sp.bev_h * sp.bev_w;
     static const int minb = getenv("OCC_SCA_MINB") ? atoi(getenv("OCC_SCA_MINB")) : 3;   // tuning knob (registers vs occupancy)
-    if (minb == 2) sca_fused_kernel<T, 2><<<ceil_div(Nq, 8), 256, 0, stream>>>(value, qproj, sp, lg, Nv, out, hits);
-    else           sca_fused_kernel<T, 3><<<ceil_div(Nq, 8), 256, 0, stream>>>(value, qproj, sp, lg, Nv, out, hits);
+    static const int tile_env = getenv("OCC_SCA_TILE") ? atoi(getenv("OCC_SCA_TILE")) : 0;
+    const int tile_mode = (tile_env && sp.bev_w % 4 == 0 && sp.bev_h % 2 == 0) ? 1 : 0;
+    if (minb == 2) sca_fused_kernel<T, 2><<<ceil_div(Nq, 8), 256, 0, stream>>>(value, qproj, sp, lg, Nv, out, hits, tile_mode);
+    else           sca_fused_kernel<T, 3><<<ceil_div(Nq, 8), 256, 0, stream>>>(value, qproj, sp, lg, Nv, out, hits, tile_mode);
     OCC_CUDA(cudaGetLastError());
     return 0;
 }
