@@ -43,6 +43,15 @@ int occb200_ms_deform_attn_forward(const float* value, const int64_t* spatial_sh
                                    const float* attn_weight, int B, int Nv, int M, int C, int Nq, int L, int P,
                                    int im2col_step, float* out, void* stream);
 
+/* Backward of the same operator (mmcv `_ext.ms_deform_attn_backward`, reference call site
+ * multi_scale_deformable_attn_function.py:150-160): grad_output dev f32 [B, Nq, M*C]; the three gradient buffers are
+ * caller-allocated and PRE-ZEROED (as the reference's autograd Function does, :146-148): grad_value [B,Nv,M,C] is
+ * accumulated with atomics, grad_sampling_loc [B,Nq,M,L,P,2] and grad_attn_weight [B,Nq,M,L,P] are written. */
+int occb200_ms_deform_attn_backward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                    const float* sampling_loc, const float* attn_weight, const float* grad_output, int B,
+                                    int Nv, int M, int C, int Nq, int L, int P, int im2col_step, float* grad_value,
+                                    float* grad_sampling_loc, float* grad_attn_weight, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * [R2] Frame engine: packs BEV queries, runs the BEVFormerEncoder layers (temporal self-attention,
  * spatial cross-attention, FFN), the Conv3d voxel decoder and the occupancy / flow heads.

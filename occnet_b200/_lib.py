@@ -25,6 +25,7 @@ SIGNATURES = {
     'occb200_last_error': (ctypes.c_char_p, []),
     'occb200_version': (ctypes.c_char_p, []),
     'occb200_ms_deform_attn_forward': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    'occb200_ms_deform_attn_backward': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     'occb200_engine_create': (_i, [ctypes.POINTER(OccConfig), ctypes.POINTER(_vp)]),
     'occb200_engine_destroy': (None, [_vp]),
     'occb200_engine_load_param': (_i, [_vp, ctypes.c_char_p, _vp, _i64]),

@@ -373,6 +373,22 @@ int occb200_ms_deform_attn_forward(const float* value, const int64_t* spatial_sh
                                P, out, (cudaStream_t)stream);
 }
 
+int occb200_ms_deform_attn_backward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                    const float* sampling_loc, const float* attn_weight, const float* grad_output, int B,
+                                    int Nv, int M, int C, int Nq, int L, int P, int im2col_step, float* grad_value,
+                                    float* grad_sampling_loc, float* grad_attn_weight, void* stream)
+{
+    OCC_CHECK(B >= 0 && Nv >= 0 && M > 0 && C > 0 && Nq >= 0 && L > 0 && P > 0, "bad sizes");
+    if ((int64_t)B * Nq == 0) return 0;
+    OCC_CHECK(value && spatial_shapes && level_start_index && sampling_loc && attn_weight && grad_output && grad_value &&
+                  grad_sampling_loc && grad_attn_weight, "null pointer");
+    const int step = im2col_step < B ? im2col_step : B;
+    OCC_CHECK(step > 0 && B % step == 0, "batch(" + std::to_string(B) + ") must divide im2col_step(" +
+                                             std::to_string(im2col_step) + ")");
+    return launch_msda_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, B, Nv, M,
+                                C, Nq, L, P, grad_value, grad_sampling_loc, grad_attn_weight, (cudaStream_t)stream);
+}
+
 int occb200_engine_create(const occb200_config* cfg, occb200_engine** out)
 {
     OCC_CHECK(cfg && out, "null pointer");

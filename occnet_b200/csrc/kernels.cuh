@@ -18,6 +18,9 @@ struct ScaParams {
 int launch_msda_forward(const float* value, const int64_t* shapes, const int64_t* lstart, const float* loc,
                         const float* wts, int B, int Nv, int M, int C, int Nq, int L, int P, float* out,
                         cudaStream_t stream);
+int launch_msda_backward(const float* value, const int64_t* shapes, const int64_t* lstart, const float* loc,
+                         const float* wts, const float* grad_out, int B, int Nv, int M, int C, int Nq, int L, int P,
+                         float* grad_value, float* grad_loc, float* grad_attn, cudaStream_t stream);
 template <typename T>
 int launch_tsa_fused(const T* value_prev, const T* value_cur, const float* qproj, int bev_h, int bev_w, T* out,
                      cudaStream_t stream);

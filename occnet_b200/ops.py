@@ -44,25 +44,53 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     return out
 
 
-def ms_deform_attn_backward(*args, **kwargs):
-    raise NotImplementedError('ms_deform_attn_backward: training is outside the inference hot path '
-                              '(SURVEY section 8f rank 4)')
+def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,
+                            grad_output, grad_value, grad_sampling_loc, grad_attn_weight, im2col_step=64):
+    """mmcv `_ext.ms_deform_attn_backward` drop-in: fills the three PRE-ZEROED gradient tensors in place."""
+    for t, n in ((value, 'value'), (sampling_locations, 'sampling_loc'), (attention_weights, 'attn_weight'),
+                 (grad_output, 'grad_output'), (grad_value, 'grad_value'), (grad_sampling_loc, 'grad_sampling_loc'),
+                 (grad_attn_weight, 'grad_attn_weight')):
+        _require(t, n, torch.float32)
+    _require(spatial_shapes, 'spatial_shapes', torch.int64)
+    _require(level_start_index, 'level_start_index', torch.int64)
+    B, Nv, M, C = value.shape
+    _, Nq, _, L, P, _ = sampling_locations.shape
+    lib = _lib.load()
+    with torch.cuda.device(value.device):
+        _lib.check(lib.occb200_ms_deform_attn_backward(
+            _lib.ptr(value), _lib.ptr(spatial_shapes), _lib.ptr(level_start_index), _lib.ptr(sampling_locations),
+            _lib.ptr(attention_weights), _lib.ptr(grad_output), B, Nv, M, C, Nq, L, P, int(im2col_step),
+            _lib.ptr(grad_value), _lib.ptr(grad_sampling_loc), _lib.ptr(grad_attn_weight), _lib.stream_ptr()))
 
 
 class MultiScaleDeformableAttnFunction_fp32(torch.autograd.Function):
-    """Forward-only drop-in for the reference autograd Function (inputs are cast to fp32 like
+    """Drop-in for the reference autograd Function, forward and backward (inputs are cast to fp32 like
     `custom_fwd(cast_inputs=torch.float32)`, multi_scale_deformable_attn_function.py:93)."""
 
     @staticmethod
     def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights,
                 im2col_step):
-        return ms_deform_attn_forward(value.float().contiguous(), value_spatial_shapes.contiguous(),
-                                      value_level_start_index.contiguous(), sampling_locations.float().contiguous(),
-                                      attention_weights.float().contiguous(), im2col_step)
+        value = value.float().contiguous()
+        sampling_locations = sampling_locations.float().contiguous()
+        attention_weights = attention_weights.float().contiguous()
+        value_spatial_shapes = value_spatial_shapes.contiguous()
+        value_level_start_index = value_level_start_index.contiguous()
+        ctx.im2col_step = im2col_step
+        out = ms_deform_attn_forward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                                     attention_weights, im2col_step)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights)
+        return out
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, grad_output):
-        ms_deform_attn_backward()
+        value, shapes, lsi, loc, aw = ctx.saved_tensors
+        grad_value = torch.zeros_like(value)
+        grad_loc = torch.zeros_like(loc)
+        grad_aw = torch.zeros_like(aw)
+        ms_deform_attn_backward(value, shapes, lsi, loc, aw, grad_output.float().contiguous(), grad_value, grad_loc,
+                                grad_aw, ctx.im2col_step)
+        return grad_value, None, None, grad_loc, grad_aw, None
 
 
 MultiScaleDeformableAttnFunction_fp16 = MultiScaleDeformableAttnFunction_fp32   # reference: both branches pick fp32

@@ -99,6 +99,37 @@ def test_ms_deform_attn_forward_error_behaviour():
     assert fn.shape == (3, 2, 8)
 
 
+@pytest.mark.parametrize('shape', [
+    dict(B=2, M=8, C=32, Nq=200, levels=[(12, 20), (6, 10), (3, 5), (2, 3)], P=8),
+    dict(B=1, M=4, C=12, Nq=33, levels=[(5, 7), (3, 3)], P=3),
+    dict(B=2, M=2, C=48, Nq=17, levels=[(6, 6)], P=4),
+])
+def test_ms_deform_attn_backward_matches_autograd_of_oracle(shape):
+    """gradients of the operator (value / sampling_loc / attn_weight) equal torch autograd through the
+    oracle's grid_sample restatement (mmcv's CPU path), fp32, tolerance 1e-3 (observed ~1e-5)."""
+    from occnet_b200 import ops
+    _, OM, _ = _oracle()
+    torch.manual_seed(1)
+    shapes = torch.tensor(shape['levels'])
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    Nv = int(shapes.prod(1).sum())
+    B, M, C, Nq, P, L = shape['B'], shape['M'], shape['C'], shape['Nq'], shape['P'], len(shape['levels'])
+    value = torch.randn(B, Nv, M, C, requires_grad=True)
+    loc = (torch.rand(B, Nq, M, L, P, 2) * 1.3 - 0.15).requires_grad_(True)       # some samples outside / on borders
+    w = torch.rand(B, Nq, M, L, P, requires_grad=True)
+    go = torch.randn(B, Nq, M * C)
+    out = OM.msda_grid_sample(value, shapes, loc, w)
+    out.backward(go)
+    vd, ld, wd = (t.detach().to(DEV).requires_grad_(True) for t in (value, loc, w))
+    got = ops.MultiScaleDeformableAttnFunction_fp32.apply(vd, shapes.to(DEV), lsi.to(DEV), ld, wd, 64)
+    np.testing.assert_allclose(got.detach().cpu().numpy(), out.detach().numpy(), atol=1e-4, rtol=0)
+    got.backward(go.to(DEV))
+    np.testing.assert_allclose(vd.grad.cpu().numpy(), value.grad.numpy(), atol=1e-3, rtol=0)
+    np.testing.assert_allclose(wd.grad.cpu().numpy(), w.grad.numpy(), atol=1e-3, rtol=0)
+    # d/d(loc) is discontinuous exactly on pixel-centre lines; random locations avoid them, tolerance scaled by the map size
+    np.testing.assert_allclose(ld.grad.cpu().numpy(), loc.grad.numpy(), atol=2e-3, rtol=1e-3)
+
+
 # ------------------------------------------------------------------------------------------ projection (a1, a2)
 @pytest.mark.parametrize('base', ['small6', 'full'])
 def test_pillar_projection_matches_point_sampling(base):
