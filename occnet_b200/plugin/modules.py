@@ -518,6 +518,18 @@ class BEVFormerOcc(BaseModule):
                                'pass img_feats=... or set feature_extractor')
         return self.feature_extractor(img)
 
+    def obtain_history_bev(self, feats_queue, img_metas_list):
+        """reference: detectors/bevformer_occ.py:159-178 -- run the encoder over the history frames (oldest first), each
+        frame's BEV feeding the next as `prev_bev`; a frame flagged `prev_bev_exists=False` restarts the recurrence.
+        `feats_queue[i]` are the FPN features of history frame i (the reference extracts them from `imgs_queue`)."""
+        prev_bev = None
+        with torch.no_grad():
+            for feats, metas in zip(feats_queue, img_metas_list):
+                if not metas[0].get('prev_bev_exists', True):
+                    prev_bev = None
+                prev_bev = self.pts_bbox_head(feats, metas, prev_bev, only_bev=True)
+        return prev_bev
+
     def simple_test_pts(self, x, img_metas, prev_bev=None, rescale=False):
         outs = self.pts_bbox_head(x, img_metas, prev_bev=prev_bev, test=True)
         occ, flow = self.pts_bbox_head.get_occ(outs, img_metas, rescale=rescale)

@@ -549,6 +549,32 @@ def test_plugin_detector_output_contract():
         det(return_loss=False, img=[torch.zeros(1, 6, 3, 64, 64, device=DEV)], img_metas=[metas])
 
 
+def test_temporal_recurrence_four_history_frames():
+    """BASELINE configs[2]: 4 history BEV frames feed the current one through `obtain_history_bev` (the TSA queue itself is
+    2: previous BEV + current, temporal_self_attention.py:195); every step rotates prev_bev by can_bus[-1]."""
+    import projects.mmdet3d_plugin  # noqa: F401
+    from occnet_b200.mmcv_shim import build_detector
+    from test_dropin_cpu import head_cfg
+    O, _, _ = _oracle()
+    cfg = fixtures.make_cfg('small6', num_layers=1, rotate_center=[20, 20])
+    params = O.init_params(cfg, seed=2)
+    det = build_detector(dict(type='BEVFormerOcc', pts_bbox_head=head_cfg(cfg))).to(DEV).eval()
+    det.pts_bbox_head.load_state_dict(params, strict=True)
+    angles = [0.0, 2.0, -3.0, 1.5, 4.0]
+    frames = [fixtures.make_feats(cfg, bs=1, seed=70 + i) for i in range(5)]
+    metas = [fixtures.make_img_metas(cfg, bs=1, can_bus_angle=a) for a in angles]
+    prev = det.obtain_history_bev([[f.to(DEV) for f in fr] for fr in frames[:4]], metas[:4])
+    _, occ, flow = det.simple_test(metas[4], img_feats=[f.to(DEV) for f in frames[4]], prev_bev=prev)
+    want_prev = None
+    with torch.no_grad():
+        for fr, m in zip(frames[:4], metas[:4]):
+            want_prev = O.head_forward(params, cfg, fr, m, prev_bev=want_prev, only_bev=True)
+        want = O.head_forward(params, cfg, frames[4], metas[4], prev_bev=want_prev)
+    assert (prev.cpu() - want_prev).abs().max().item() < 1e-3
+    assert (flow.cpu() - want['flow']).abs().max().item() < 1e-3
+    assert (occ.cpu() == want['occ'].argmax(-1)).float().mean().item() > 0.9995
+
+
 def test_plugin_ray_metrics_main_matches_oracle():
     from projects.mmdet3d_plugin.datasets import ray_metrics as rm
     _, _, ORM = _oracle()
