@@ -9,14 +9,23 @@ namespace {
 
 // [cam][C][hw] f32 -> [cam][Nv][C] T (+ cams_embeds[cam][c], then + level_embed[c]; same order as the reference).
 // 64 (pixels) x 64 (channels) tile per CTA: float4 reads along the pixel axis, 16-byte (8 x bf16) writes along C.
+// All FPN levels in one launch: blockIdx.x walks the 64-pixel tiles of level 0, then level 1, ...
 template <typename T>
 __global__ void __launch_bounds__(256)
-pack_level_kernel(const float* __restrict__ feat, const float* __restrict__ cams_embeds,
-                  const float* __restrict__ level_embed, int C, int hw, int Nv, int start, T* __restrict__ tokens)
+pack_levels_kernel(PackLevels pl, const float* __restrict__ cams_embeds, const float* __restrict__ level_embeds, int C,
+                   int Nv, T* __restrict__ tokens)
 {
     __shared__ float tile[64][65];                             // [channel][pixel], padded
+    int lvl = 0;
+#pragma unroll
+    for (int l = 1; l < 8; ++l) if (l < pl.num_levels && (int)blockIdx.x >= pl.tile_begin[l]) lvl = l;
+    const float* feat = nullptr; int hw = 0, start = 0, tb = 0;
+#pragma unroll
+    for (int l = 0; l < 8; ++l)                                // static selects (no dynamically indexed parameter copy)
+        if (l == lvl) { feat = pl.feat[l]; hw = pl.hw[l]; start = pl.start[l]; tb = pl.tile_begin[l]; }
+    const float* level_embed = level_embeds + lvl * C;
     const int cam = blockIdx.z;
-    const int p0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+    const int p0 = ((int)blockIdx.x - tb) * 64, c0 = blockIdx.y * 64;
     const int tid = threadIdx.x;
     const float* src = feat + (int64_t)cam * C * hw;
     const bool vec_ok = (hw & 3) == 0;
@@ -156,19 +165,27 @@ __global__ void cast_kernel(const float* __restrict__ s, T* __restrict__ d, int6
 }  // namespace
 
 template <typename T>
-int launch_pack_level(const float* feat, const float* cams_embeds, const float* level_embed, int num_cams, int C,
-                      int hw, int Nv, int start, T* tokens, cudaStream_t stream)
+int launch_pack_levels(const float* const* feats, const LevelGeom& lg, const float* cams_embeds, const float* level_embeds,
+                       int num_cams, int C, int Nv, T* tokens, cudaStream_t stream)
 {
-    OCC_CHECK(C % 64 == 0, "pack_level: C must be a multiple of 64");
-    dim3 grid(ceil_div(hw, 64), C / 64, num_cams);
-    pack_level_kernel<T><<<grid, 256, 0, stream>>>(feat, cams_embeds, level_embed, C, hw, Nv, start, tokens);
+    OCC_CHECK(C % 64 == 0, "pack_levels: C must be a multiple of 64");
+    OCC_CHECK(lg.num_levels >= 1 && lg.num_levels <= 8, "pack_levels: 1..8 levels");
+    PackLevels pl{};
+    pl.num_levels = lg.num_levels;
+    int tiles = 0;
+    for (int l = 0; l < lg.num_levels; ++l) {
+        pl.feat[l] = feats[l]; pl.hw[l] = lg.h[l] * lg.w[l]; pl.start[l] = lg.start[l]; pl.tile_begin[l] = tiles;
+        tiles += ceil_div(pl.hw[l], 64);
+    }
+    dim3 grid(tiles, C / 64, num_cams);
+    pack_levels_kernel<T><<<grid, 256, 0, stream>>>(pl, cams_embeds, level_embeds, C, Nv, tokens);
     OCC_CUDA(cudaGetLastError());
     return 0;
 }
-template int launch_pack_level<float>(const float*, const float*, const float*, int, int, int, int, int, float*,
-                                      cudaStream_t);
-template int launch_pack_level<bf16>(const float*, const float*, const float*, int, int, int, int, int, bf16*,
-                                     cudaStream_t);
+template int launch_pack_levels<float>(const float* const*, const LevelGeom&, const float*, const float*, int, int, int,
+                                       float*, cudaStream_t);
+template int launch_pack_levels<bf16>(const float* const*, const LevelGeom&, const float*, const float*, int, int, int,
+                                      bf16*, cudaStream_t);
 
 template <typename T>
 int launch_layernorm(const float* x, const float* gamma, const float* beta, const float* pos, int rows, int C,

@@ -65,6 +65,7 @@ struct occb200_engine {
     std::map<std::string, std::vector<float>> host_params;
     std::vector<LayerW> layers;
     DevBuf bev_queries, pos, pos_t32, cams_embeds, level_embeds;
+    DevBuf qc_f32, qc_t, qc_pos_t;      // parameter-only layer-0 operands (query fp32 T32, bf16 query, bf16 query+pos), built once
     DevBuf conv_w[2], conv_b[2], conv_wh[2];
     DevBuf sca_v_all_wh, sca_v_all_b, sca_value_all;     // value_proj of every layer, concatenated (tensor-core path)
     DevBuf hw1, hb1, hw2, hb2, fw1, fb1, fw2, fb2, head_w1h, head_w2h, head_b1c, head_b2c;
@@ -156,8 +157,12 @@ int gemm(occb200_engine* e, const TA* A, const TA* A2, int K1, const float* W, c
                                reinterpret_cast<const bf16*>(Wh), bias, residual, C, M, N, K, act, st);
         }
     }
-    const int lda = A2 ? K1 : K;
-    return gemm_simt<TA, TC>(A, lda, A2, A2 ? K - K1 : 0, K1, W, bias, residual, N, C, N, M, N, K, act, st);
+    if constexpr (std::is_same<TC, __half>::value) {
+        OCC_CHECK(false, "gemm: fp16 outputs exist only on the tensor-core path");
+    } else {
+        const int lda = A2 ? K1 : K;
+        return gemm_simt<TA, TC>(A, lda, A2, A2 ? K - K1 : 0, K1, W, bias, residual, N, C, N, M, N, K, act, st);
+    }
 }
 
 // y = LayerNorm(A.W^T + b + residual): one tcgen05 kernel (GEMM with LayerNorm epilogue) on the tensor-core path
@@ -178,10 +183,10 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
     const int Nq = e->Nq, Nv = e->Nv, C = 256, ncam = c.num_cams;
     e->launches = 0;
     T* tokens = e->tokens.as<T>();
-    for (int l = 0; l < c.num_levels; ++l) {
+    {
         ProfScope ps(e, st, CAT_PACK);
-        if (launch_pack_level<T>(feats[l], e->cams_embeds.as<float>(), e->level_embeds.as<float>() + l * C, ncam, C,
-                                 e->lg.h[l] * e->lg.w[l], Nv, e->lg.start[l], tokens, st)) return 2;
+        if (launch_pack_levels<T>(feats, e->lg, e->cams_embeds.as<float>(), e->level_embeds.as<float>(), ncam, C, Nv, tokens,
+                                  st)) return 2;
         e->launches++;
     }
     float* q_f32 = e->q_f32.as<float>();
@@ -192,21 +197,51 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
     // tensor-core path: LayerNorm is fused into the GEMM epilogues and the fp32 residual stream lives in the T32 layout
     const bool fuse_ln = sizeof(T) == 2 && c.use_tensor_cores && !e->taps && e->pos_t32.p != nullptr &&
                          e->layers[0].tsa_o_wh.p != nullptr;
-    {
+    // Layer-0 operands.  On the fused tensor-core path they were built once at finalize (parameters only); the
+    // residual stream then rotates through {constant, q_f32, x_f32} without ever writing the constant buffer.
+    const bool const_q = fuse_ln && e->qc_f32.p != nullptr;
+    const float* const qc_f32 = const_q ? e->qc_f32.as<float>() : nullptr;
+    float* spare_f32 = nullptr;
+    const T* q_in = q_t;                    // bf16/fp32 operand copy of the current query
+    const T* q_pos_in = q_pos_t;            // ... of query + pos
+    if (const_q) {
+        q_in = e->qc_t.as<T>(); q_pos_in = e->qc_pos_t.as<T>();
+        spare_f32 = x_f32; x_f32 = q_f32; q_f32 = e->qc_f32.as<float>();     // q_f32 is only READ until advance()
+    } else {
         ProfScope ps(e, st, CAT_PACK);
         if (launch_prepare_query<T>(e->bev_queries.as<float>(), pos, (int64_t)Nq * C, q_f32, q_t, q_pos_t, fuse_ln ? 1 : 0,
                                     st)) return 2;
+        e->launches++;
     }
-    e->launches++;
+    auto advance = [&]() {                  // the LayerNorm output just written to x_f32 becomes the residual stream
+        float* old = q_f32;
+        q_f32 = x_f32;
+        x_f32 = (old == qc_f32) ? spare_f32 : old;
+    };
     const bool has_prev = prev_bev != nullptr;
+    const T* q0_t = nullptr;
     if (has_prev) {
         // encoder.py:204-209: value = stack([prev_bev, bev_query]) built ONCE before the layer loop, so
         // queue 1 keeps seeing the layer-0 query in every layer.
         if (launch_cast<T>(prev_bev, e->prev_t.as<T>(), (int64_t)Nq * C, st)) return 2;
-        if (launch_cast<T>(e->bev_queries.as<float>(), e->q0_t.as<T>(), (int64_t)Nq * C, st)) return 2;
-        e->launches += 2;
+        e->launches++;
+        if (const_q) {
+            q0_t = e->qc_t.as<T>();
+        } else {
+            if (launch_cast<T>(e->bev_queries.as<float>(), e->q0_t.as<T>(), (int64_t)Nq * C, st)) return 2;
+            e->launches++;
+            q0_t = e->q0_t.as<T>();
+        }
     }
-    float* qproj = e->qproj.as<float>();
+    // sampling offsets / attention logits: fp16 on the tensor-core path (half the bytes between the projection GEMM and
+    // the gather kernel; |offset| is a few pixels, so fp16's 11-bit mantissa keeps locations to < 0.01 px), fp32 otherwise
+    const int nq_tsa = 2 * 8 * c.tsa_points * 3;   // offsets (x,y) + logits
+    const int nq_sca = 8 * c.num_levels * c.sca_points * 3;
+    static const bool q_f32_env = getenv("OCC_QPROJ_F32") != nullptr;
+    const bool q_half = sizeof(T) == 2 && c.use_tensor_cores && !q_f32_env && e->layers[0].tsa_q_wh.p != nullptr &&
+                        e->layers[0].sca_q_wh.p != nullptr && gemm_tc_supported(Nq, nq_tsa, 2 * C, C) &&
+                        gemm_tc_supported(Nq, nq_sca, C, C);
+    void* qproj = e->qproj.p;
     T* attn_out = e->attn_out.as<T>();
     const bool hoist_v = sizeof(T) == 2 && c.use_tensor_cores && e->sca_value_all.p != nullptr;
     if (hoist_v) {
@@ -220,25 +255,31 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
         // ---- temporal self-attention (temporal_self_attention.py:177-272)
         T* v_cur = e->tsa_value.as<T>();
         T* v_prev = v_cur;
-        if (gemm<T, T>(e, has_prev ? e->q0_t.as<T>() : q_t, nullptr, 0, w.tsa_v_w.as<float>(), w.tsa_v_wh.p,
+        if (gemm<T, T>(e, has_prev ? q0_t : q_in, nullptr, 0, w.tsa_v_w.as<float>(), w.tsa_v_wh.p,
                        w.tsa_v_b.as<float>(), nullptr, v_cur, Nq, C, C, ACT_NONE, st)) return 2;
         if (has_prev) {
             v_prev = e->tsa_value_prev.as<T>();
             if (gemm<T, T>(e, e->prev_t.as<T>(), nullptr, 0, w.tsa_v_w.as<float>(), w.tsa_v_wh.p,
                            w.tsa_v_b.as<float>(), nullptr, v_prev, Nq, C, C, ACT_NONE, st)) return 2;
         }
-        const int nq_tsa = 2 * 8 * c.tsa_points * 3;   // offsets (x,y) + logits
-        if (gemm<T, float>(e, has_prev ? e->prev_t.as<T>() : q_t, q_pos_t, C, w.tsa_q_w.as<float>(), w.tsa_q_wh.p,
-                           w.tsa_q_b.as<float>(), nullptr, qproj, Nq, nq_tsa, 2 * C, ACT_NONE, st)) return 2;
+        {
+            const T* qa = has_prev ? e->prev_t.as<T>() : q_in;
+            const int rc = q_half ? gemm<T, __half>(e, qa, q_pos_in, C, w.tsa_q_w.as<float>(), w.tsa_q_wh.p, w.tsa_q_b.as<float>(),
+                                                    nullptr, (__half*)qproj, Nq, nq_tsa, 2 * C, ACT_NONE, st)
+                                  : gemm<T, float>(e, qa, q_pos_in, C, w.tsa_q_w.as<float>(), w.tsa_q_wh.p, w.tsa_q_b.as<float>(),
+                                                   nullptr, (float*)qproj, Nq, nq_tsa, 2 * C, ACT_NONE, st);
+            if (rc) return 2;
+        }
         {
             ProfScope ps(e, st, CAT_TSA);
-            if (launch_tsa_fused<T>(v_prev, v_cur, qproj, c.bev_h, c.bev_w, attn_out, st)) return 2;
+            if (launch_tsa_fused<T>(v_prev, v_cur, qproj, q_half, c.bev_h, c.bev_w, attn_out, st)) return 2;
         }
         e->launches++;
         if (fuse_ln) {
             if (gemm_ln_fused(e, (const bf16*)attn_out, w.tsa_o_wh.p, w.tsa_o_b.as<float>(), q_f32, w.ln_g[0].as<float>(),
                               w.ln_b[0].as<float>(), nullptr, x_f32, (bf16*)q_t, nullptr, Nq, C, st)) return 2;
-            std::swap(q_f32, x_f32);
+            advance();
+            q_in = q_t; q_pos_in = q_pos_t;
         } else {
             if (gemm<T, float>(e, attn_out, nullptr, 0, w.tsa_o_w.as<float>(), w.tsa_o_wh.p, w.tsa_o_b.as<float>(),
                                q_f32, x_f32, Nq, C, C, ACT_NONE, st)) return 2;
@@ -253,9 +294,13 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
             e->launches++;
         }
         // ---- spatial cross-attention (spatial_cross_attention.py:128-175, :334-393)
-        const int nq_sca = 8 * c.num_levels * c.sca_points * 3;
-        if (gemm<T, float>(e, q_t, nullptr, 0, w.sca_q_w.as<float>(), w.sca_q_wh.p, w.sca_q_b.as<float>(), nullptr,
-                           qproj, Nq, nq_sca, C, ACT_NONE, st)) return 2;
+        {
+            const int rc = q_half ? gemm<T, __half>(e, q_t, nullptr, 0, w.sca_q_w.as<float>(), w.sca_q_wh.p, w.sca_q_b.as<float>(),
+                                                    nullptr, (__half*)qproj, Nq, nq_sca, C, ACT_NONE, st)
+                                  : gemm<T, float>(e, q_t, nullptr, 0, w.sca_q_w.as<float>(), w.sca_q_wh.p, w.sca_q_b.as<float>(),
+                                                   nullptr, (float*)qproj, Nq, nq_sca, C, ACT_NONE, st);
+            if (rc) return 2;
+        }
         const T* sca_val = e->sca_value.as<T>();
         if (hoist_v) {
             sca_val = reinterpret_cast<const T*>(e->sca_value_all.as<bf16>() + (size_t)l * ncam * Nv * C);
@@ -263,13 +308,13 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
                               e->sca_value.as<T>(), ncam * Nv, C, C, ACT_NONE, st)) return 2;
         {
             ProfScope ps(e, st, CAT_SCA);
-            if (launch_sca_fused<T>(sca_val, qproj, e->sp, e->lg, Nv, attn_out, e->hits.as<uint8_t>(), st)) return 2;
+            if (launch_sca_fused<T>(sca_val, qproj, q_half, e->sp, e->lg, Nv, attn_out, e->hits.as<uint8_t>(), st)) return 2;
         }
         e->launches++;
         if (fuse_ln) {
             if (gemm_ln_fused(e, (const bf16*)attn_out, w.sca_o_wh.p, w.sca_o_b.as<float>(), q_f32, w.ln_g[1].as<float>(),
                               w.ln_b[1].as<float>(), nullptr, x_f32, (bf16*)q_t, nullptr, Nq, C, st)) return 2;
-            std::swap(q_f32, x_f32);
+            advance();
         } else {
             if (gemm<T, float>(e, attn_out, nullptr, 0, w.sca_o_w.as<float>(), w.sca_o_wh.p, w.sca_o_b.as<float>(),
                                q_f32, x_f32, Nq, C, C, ACT_NONE, st)) return 2;
@@ -290,7 +335,7 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
             if (gemm_ln_fused(e, e->ffn_h.as<bf16>(), w.ffn2_wh.p, w.ffn2_b.as<float>(), q_f32, w.ln_g[2].as<float>(),
                               w.ln_b[2].as<float>(), e->pos_t32.as<float>(), x_f32, (bf16*)q_t, (bf16*)q_pos_t, Nq, c.ffn_dim, st))
                 return 2;
-            std::swap(q_f32, x_f32);
+            advance();
         } else {
             if (gemm<T, float>(e, e->ffn_h.as<T>(), nullptr, 0, w.ffn2_w.as<float>(), w.ffn2_wh.p, w.ffn2_b.as<float>(),
                                q_f32, x_f32, Nq, C, c.ffn_dim, ACT_NONE, st)) return 2;
@@ -308,7 +353,7 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
     if (fuse_ln) {                                                 // back to row-major for the outputs / voxel decoder
         ProfScope ps(e, st, CAT_PACK);
         if (launch_t32_convert(q_f32, x_f32, Nq, 1, st)) return 2;
-        std::swap(q_f32, x_f32);
+        advance();
         e->launches++;
     }
     if (bev_embed)
@@ -432,7 +477,7 @@ void occb200_engine_destroy(occb200_engine* e)
                          &w.tsa_q_wh, &w.tsa_o_wh, &w.sca_q_wh, &w.sca_v_wh, &w.sca_o_wh, &w.ffn1_wh, &w.ffn2_wh};
         for (DevBuf* b : all) b->release();
     }
-    DevBuf* all[] = {&e->bev_queries, &e->pos, &e->pos_t32, &e->cams_embeds, &e->level_embeds, &e->conv_w[0], &e->conv_w[1],
+    DevBuf* all[] = {&e->qc_f32, &e->qc_t, &e->qc_pos_t, &e->bev_queries, &e->pos, &e->pos_t32, &e->cams_embeds, &e->level_embeds, &e->conv_w[0], &e->conv_w[1],
                      &e->conv_b[0], &e->conv_b[1], &e->conv_wh[0], &e->conv_wh[1], &e->sca_v_all_wh, &e->sca_v_all_b, &e->sca_value_all, &e->hw1, &e->hb1, &e->hw2, &e->hb2,
                      &e->fw1, &e->fb1, &e->fw2, &e->fb2, &e->head_w1h, &e->head_w2h, &e->head_b1c, &e->head_b2c, &e->tokens, &e->sca_value, &e->q_f32, &e->q_t,
                      &e->q_pos_t, &e->q0_t, &e->prev_t, &e->tsa_value, &e->tsa_value_prev, &e->qproj, &e->attn_out,
@@ -485,6 +530,12 @@ int occb200_engine_finalize(occb200_engine* e)
             if (e->pos_t32.alloc(rows_pad * C * 4)) return 2;
             OCC_CUDA(cudaMemset(e->pos_t32.p, 0, rows_pad * C * 4));
             if (launch_t32_convert(e->pos.as<float>(), e->pos_t32.as<float>(), Nq, 0, 0)) return 2;
+            // bev_queries / pos are parameters: their fp32 (T32) and bf16 operand forms are frame-independent
+            if (e->qc_f32.alloc(rows_pad * C * 4) || e->qc_t.alloc((size_t)Nq * C * 2) || e->qc_pos_t.alloc((size_t)Nq * C * 2))
+                return 2;
+            OCC_CUDA(cudaMemset(e->qc_f32.p, 0, rows_pad * C * 4));
+            if (launch_prepare_query<bf16>(e->bev_queries.as<float>(), e->pos.as<float>(), (int64_t)Nq * C, e->qc_f32.as<float>(),
+                                           e->qc_t.as<bf16>(), e->qc_pos_t.as<bf16>(), 1, 0)) return 2;
         }
         OCC_CUDA(cudaDeviceSynchronize());
         dre.release(); dce.release();

@@ -16,6 +16,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <type_traits>
 #include <vector>
 
 #include "gemm_tc.cuh"
@@ -367,9 +368,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             // default (ldc = N, nblk_stride = BN) is the plain row-major [M,N]; the blocked form
                             // writes each n-block as its own contiguous [M,BN] matrix (per-layer value buffers)
                             const size_t o = (size_t)n_blk * nblk_stride + (size_t)grow * ldc + c0 + cpiece * 4;
-                            if constexpr (sizeof(TC) == 4) *reinterpret_cast<float4*>(reinterpret_cast<float*>(C) + o) = v;
-                            else *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(C) + o) =
-                                     make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+                            if constexpr (sizeof(TC) == 4) {
+                                *reinterpret_cast<float4*>(reinterpret_cast<float*>(C) + o) = v;
+                            } else if constexpr (std::is_same<TC, __half>::value) {
+                                const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+                                *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(C) + o) =
+                                    make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+                            } else {
+                                *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(C) + o) =
+                                    make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+                            }
                         }
                     }
                     __syncwarp();
@@ -549,5 +557,7 @@ template int gemm_tc<float>(const bf16*, const bf16*, int, const bf16*, const fl
                             int, int, cudaStream_t);
 template int gemm_tc<bf16>(const bf16*, const bf16*, int, const bf16*, const float*, const float*, bf16*, int, int, int,
                            int, cudaStream_t);
+template int gemm_tc<__half>(const bf16*, const bf16*, int, const bf16*, const float*, const float*, __half*, int, int, int,
+                             int, cudaStream_t);
 
 }  // namespace occ

@@ -22,18 +22,20 @@ int launch_msda_backward(const float* value, const int64_t* shapes, const int64_
                          const float* wts, const float* grad_out, int B, int Nv, int M, int C, int Nq, int L, int P,
                          float* grad_value, float* grad_loc, float* grad_attn, cudaStream_t stream);
 template <typename T>
-int launch_tsa_fused(const T* value_prev, const T* value_cur, const float* qproj, int bev_h, int bev_w, T* out,
-                     cudaStream_t stream);
+int launch_tsa_fused(const T* value_prev, const T* value_cur, const void* qproj, bool qproj_is_half, int bev_h, int bev_w,
+                     T* out, cudaStream_t stream);
 template <typename T>
-int launch_sca_fused(const T* value, const float* qproj, const ScaParams& sp, const LevelGeom& lg, int Nv, T* out,
-                     uint8_t* hits, cudaStream_t stream);
+int launch_sca_fused(const T* value, const void* qproj, bool qproj_is_half, const ScaParams& sp, const LevelGeom& lg, int Nv,
+                     T* out, uint8_t* hits, cudaStream_t stream);
 int launch_project_pillars(const ScaParams& sp, float* ref_cam, uint8_t* mask, cudaStream_t stream);
 
 // ---- elementwise.cu
 // feats level l: [num_cams, C, h, w] f32 (NCHW) -> tokens [num_cams, Nv, C] T, + cams_embeds + level_embeds
+// (all levels in one launch; level_embeds [num_levels, C])
+struct PackLevels { const float* feat[8]; int hw[8], start[8], tile_begin[8], num_levels; };
 template <typename T>
-int launch_pack_level(const float* feat, const float* cams_embeds, const float* level_embed, int num_cams, int C,
-                      int hw, int Nv, int start, T* tokens, cudaStream_t stream);
+int launch_pack_levels(const float* const* feats, const LevelGeom& lg, const float* cams_embeds, const float* level_embeds,
+                       int num_cams, int C, int Nv, T* tokens, cudaStream_t stream);
 // y = LayerNorm(x) (eps 1e-5); writes fp32 copy (residual stream), T copy (GEMM operand) and T copy of y + pos
 template <typename T>
 int launch_layernorm(const float* x, const float* gamma, const float* beta, const float* pos, int rows, int C,

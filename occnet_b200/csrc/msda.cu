@@ -15,6 +15,8 @@
 // a lane accumulates 8 of the head's 32 channels, so one warp-wide 128-bit load instruction
 // fetches 8 independent 64-byte (bf16) corner rows.  Per-sample scalars (location, weight) live
 // in one owner lane per (head, level) and are broadcast inside the 4-lane group with shuffles.
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 
 #include "common.cuh"
@@ -65,7 +67,7 @@ constexpr int CODE_VALID = 1 << 30, CODE_OFF_MASK = CODE_VALID - 1;
 // base, base+1 pixel, base+1 row, base+1 row+1 pixel with CONSTANT strides (no per-sample border flags, no branches).
 // The bilinear corner weights are assigned to the positions of that block that coincide with in-bounds true corners
 // (zero padding for the others); for interior samples this is exactly the usual (hh*hw, hh*lw, lh*hw, lh*lw).
-__device__ __forceinline__ SamplePrep prep_sample(float h_im, float w_im, float wt, int H, int W)
+__device__ __forceinline__ SamplePrep prep_sample(float h_im, float w_im, float wt, int H, int W, int base_pix = 0)
 {
     SamplePrep s;
     const bool valid = h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W;   // mmcv kernel's test
@@ -79,7 +81,7 @@ __device__ __forceinline__ SamplePrep prep_sample(float h_im, float w_im, float 
     const float cw1 = (w_lo == wb + 1) ? hw : ((w_lo == wb) ? lw : 0.f);
     const float g = valid ? wt : 0.f;
     s.c1 = g * (rw0 * cw0); s.c2 = g * (rw0 * cw1); s.c3 = g * (rw1 * cw0); s.c4 = g * (rw1 * cw1);
-    s.code = (hb * W + wb) | (valid ? CODE_VALID : 0);
+    s.code = (base_pix + hb * W + wb) | (valid ? CODE_VALID : 0);
     return s;
 }
 
@@ -190,6 +192,177 @@ __device__ __forceinline__ void shuffle_gather(Acc<T>& acc, const T* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------
+// bf16 production path: descriptor-staged, software-pipelined gather.
+//   Phase 1: the owner lanes write one 16-byte descriptor per sample {pixel | VALID, w1|w2, w3|w4, -} to shared memory,
+//            laid out [sample][head] (one conflict-free 128-byte row per sample).
+//   Phase 2: the 4 lanes of a head walk their NS descriptors (one broadcast LDS.128 each, no shuffles); the four
+//            128-bit corner loads of sample i+DEPTH are issued BEFORE the 32 FHFMAs of sample i, so every lane keeps
+//            4*DEPTH independent loads in flight -- the previous version waited on each sample's loads (ncu: 5.5 of 10
+//            stall cycles per issue were long-scoreboard) because the validity branch fenced the loads.
+// geom(i, base, W): value pointer (already offset to this lane's head / channel slice) and row pitch of sample i.
+template <int NS, int DEPTH, typename Geom>
+__device__ __forceinline__ void gather_descs(float (&acc)[8], const uint4* dsm, Geom geom)
+{
+    uint4 d[DEPTH + 1];
+    uint4 v[DEPTH + 1][4];
+#pragma unroll
+    for (int i = 0; i < NS + DEPTH; ++i) {
+        if (i < NS) {
+            const int slot = i % (DEPTH + 1);
+            d[slot] = dsm[i * 8];
+            const bf16* base; int W;
+            geom(i, base, W);
+            if (d[slot].x & CODE_VALID) {
+                const bf16* p = base + (int64_t)(d[slot].x & CODE_OFF_MASK) * 256;
+                const bf16* pr = p + (int64_t)W * 256;
+                v[slot][0] = __ldg(reinterpret_cast<const uint4*>(p));
+                v[slot][1] = __ldg(reinterpret_cast<const uint4*>(p + 256));
+                v[slot][2] = __ldg(reinterpret_cast<const uint4*>(pr));
+                v[slot][3] = __ldg(reinterpret_cast<const uint4*>(pr + 256));
+            }
+        }
+        if (i >= DEPTH) {
+            const int slot = (i - DEPTH) % (DEPTH + 1);
+            if (d[slot].x & CODE_VALID) {
+                fma_word4(acc, v[slot][0], d[slot].y); fma_word4(acc, v[slot][1], d[slot].y >> 16);
+                fma_word4(acc, v[slot][2], d[slot].z); fma_word4(acc, v[slot][3], d[slot].z >> 16);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void project_point(const float* __restrict__ m, float xs, float ys, float zs,
+                                              const ScaParams& sp, float& u, float& v, bool& ok);
+
+// N consecutive query-projection outputs (fp32, or fp16 when the tensor-core GEMM writes them in half precision)
+template <int N>
+__device__ __forceinline__ void load_q(const float* __restrict__ p, float (&o)[N])
+{
+    if constexpr (N == 2) {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+        o[0] = t.x; o[1] = t.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < N / 4; ++i) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
+            o[4 * i] = t.x; o[4 * i + 1] = t.y; o[4 * i + 2] = t.z; o[4 * i + 3] = t.w;
+        }
+    }
+}
+template <int N>
+__device__ __forceinline__ void load_q(const __half* __restrict__ p, float (&o)[N])
+{
+    if constexpr (N == 2) {
+        const uint32_t t = __ldg(reinterpret_cast<const uint32_t*>(p));
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&t));
+        o[0] = f.x; o[1] = f.y;
+    } else if constexpr (N == 4) {
+        const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+        o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < N / 8; ++i) {
+            const uint4 t = __ldg(reinterpret_cast<const uint4*>(p) + i);
+            const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+                o[8 * i + 2 * j] = f.x; o[8 * i + 2 * j + 1] = f.y;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ uint4 make_desc(const SamplePrep& sm)
+{
+    return make_uint4((uint32_t)sm.code, pack_bf16x2(sm.c1, sm.c2), pack_bf16x2(sm.c3, sm.c4), 0u);
+}
+
+template <typename QT, int DEPTH, int MINB, int NW>
+__global__ void __launch_bounds__(NW * 32, MINB)
+sca_pipe_kernel(const bf16* __restrict__ value, const QT* __restrict__ qproj, ScaParams sp, LevelGeom lg,
+                int Nv, bf16* __restrict__ out, uint8_t* __restrict__ hits)
+{
+    __shared__ uint4 descs[NW][32 * 8];                          // [warp][sample = point*4 + level][head]
+    const int Nq = sp.bev_h * sp.bev_w;
+    const int q = blockIdx.x * NW + (threadIdx.x >> 5);
+    if (q >= Nq) return;
+    const int lane = threadIdx.x & 31, head = lane >> 2, s = lane & 3;   // s doubles as the owned level
+    const unsigned FULL = 0xffffffffu;
+
+    const float xs = __fdiv_rn((float)(q % sp.bev_w) + 0.5f, (float)sp.bev_w);
+    const float ys = __fdiv_rn((float)(q / sp.bev_w) + 0.5f, (float)sp.bev_h);
+    float ru[2], rv[2];
+    unsigned vis = 0;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int c = r * 4 + (lane >> 3), z = lane & 7;
+        bool ok = false;
+        ru[r] = 0.f; rv[r] = 0.f;
+        if (c < sp.num_cams && z < sp.D) project_point(sp.cam_mat[c], xs, ys, sp.zs[z], sp, ru[r], rv[r], ok);
+        const unsigned b = __ballot_sync(FULL, ok);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if ((b >> (8 * k)) & 0xffu) vis |= 1u << (r * 4 + k);
+    }
+    const int count = __popc(vis);
+    if (hits && lane == 0) hits[q] = (uint8_t)count;
+
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    uint4* dw = descs[threadIdx.x >> 5];
+    const int own_W = s == 0 ? lg.w[0] : s == 1 ? lg.w[1] : s == 2 ? lg.w[2] : lg.w[3];
+    const int own_H = s == 0 ? lg.h[0] : s == 1 ? lg.h[1] : s == 2 ? lg.h[2] : lg.h[3];
+    const int own_start = s == 0 ? lg.start[0] : s == 1 ? lg.start[1] : s == 2 ? lg.start[2] : lg.start[3];
+    const float own_w = (float)own_W, own_h = (float)own_H;
+
+    for (int c = 0; c < sp.num_cams; ++c) {
+        if (!((vis >> c) & 1u)) continue;                                // warp-uniform
+        // ---- phase 1: my (head, level s): 8 offsets + 8 logits -> 8 descriptors.  (Reloaded per visible camera --
+        // 1.2 on average -- so that nothing but the accumulators stays live across the gather.)
+        {
+            const QT* qp = qproj + (int64_t)q * 768;
+            float off[16], wl[8];
+            load_q<16>(qp + head * 64 + s * 16, off);
+            load_q<8>(qp + 512 + head * 32 + s * 8, wl);
+            float mx = wl[0];
+#pragma unroll
+            for (int i = 1; i < 8; ++i) mx = fmaxf(mx, wl[i]);
+            mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 2));
+            float sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { wl[i] = __expf(wl[i] - mx); sum += wl[i]; }
+            sum += __shfl_xor_sync(FULL, sum, 1);
+            sum += __shfl_xor_sync(FULL, sum, 2);
+            const float inv = __fdividef(1.f, sum);
+            const int r = c >> 2;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                const int asrc = (c & 3) * 8 + (p % sp.D);               // Z-anchor interleave (:366-373)
+                const float u = __shfl_sync(FULL, r ? ru[1] : ru[0], asrc);
+                const float v = __shfl_sync(FULL, r ? rv[1] : rv[0], asrc);
+                // (u + dx/W) * W - 0.5 == u*W + dx - 0.5 up to fp32 rounding (bf16 path: not bit-matched to the fp32 one)
+                const float w_im = fmaf(u, own_w, off[2 * p] - 0.5f);
+                const float h_im = fmaf(v, own_h, off[2 * p + 1] - 0.5f);
+                dw[(p * 4 + s) * 8 + head] = make_desc(prep_sample(h_im, w_im, wl[p] * inv, own_H, own_W, own_start));
+            }
+        }
+        __syncwarp();
+        // ---- phase 2
+        const bf16* vcam = value + ((int64_t)c * Nv * 8 + head) * 32 + s * 8;
+        gather_descs<32, DEPTH>(acc, dw + head, [&](int i, const bf16*& base, int& W) { base = vcam; W = lg.w[i & 3]; });
+        __syncwarp();
+    }
+    const float scale = (float)max(count, 1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = __fdiv_rn(acc[i], scale);
+    store8(out + (int64_t)q * 256 + head * 32 + s * 8, acc);
+}
+
+// ------------------------------------------------------------------------------------------
 // Operator boundary: value [B,Nv,M,C] f32, loc [B,Nq,M,L,P,2] (x,y), w [B,Nq,M,L,P] -> [B,Nq,M*C]
 // One thread per (b, q, head, 8-channel slice) when C % 8 == 0, otherwise per channel.
 template <int VEC>
@@ -246,20 +419,23 @@ __global__ void msda_forward_kernel(const float* __restrict__ value, const int64
 //   [128,192): attention logits viewed (head, queue, point), softmax over the 4 points (:209-211)
 // value_prev / value_cur: [Nq, 8, 32] T (projected values of queue 0 / queue 1).
 // out[q] = 0.5 * (MSDA_queue0 + MSDA_queue1)                                (:257-262)
-template <typename T>
+template <typename T, typename QT>
 __global__ void __launch_bounds__(256)
 tsa_fused_kernel(const T* __restrict__ value_prev, const T* __restrict__ value_cur,
-                 const float* __restrict__ qproj, int bev_h, int bev_w, T* __restrict__ out)
+                 const QT* __restrict__ qproj, int bev_h, int bev_w, T* __restrict__ out)
 {
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int Nq = bev_h * bev_w;
     if (q >= Nq) return;
     const int lane = threadIdx.x & 31, head = lane >> 2, s = lane & 3;
     const int qu_own = s >> 1, p0 = (s & 1) * 2;              // owner of samples (queue, p0), (queue, p0+1)
-    const float* qp = qproj + (int64_t)q * 192;
-    // offsets of my two samples: index head*16 + queue*8 + p*2 + xy -> 4 consecutive floats
-    const float4 off = __ldg(reinterpret_cast<const float4*>(qp + head * 16 + qu_own * 8 + p0 * 2));
-    const float2 lg = __ldg(reinterpret_cast<const float2*>(qp + 128 + head * 8 + qu_own * 4 + p0));
+    const QT* qp = qproj + (int64_t)q * 192;
+    // offsets of my two samples: index head*16 + queue*8 + p*2 + xy -> 4 consecutive values
+    float offv[4], lgv[2];
+    load_q<4>(qp + head * 16 + qu_own * 8 + p0 * 2, offv);
+    load_q<2>(qp + 128 + head * 8 + qu_own * 4 + p0, lgv);
+    const float4 off = make_float4(offv[0], offv[1], offv[2], offv[3]);
+    const float2 lg = make_float2(lgv[0], lgv[1]);
     // softmax over the 4 points of (head, queue): my 2 logits + partner lane (s ^ 1)
     float mx = fmaxf(lg.x, lg.y);
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
@@ -332,17 +508,13 @@ __global__ void project_pillars_kernel(ScaParams sp, float* __restrict__ ref_cam
 //   value [num_cams, Nv, 8, 32] T;  qproj [Nq, 768] f32 = [offsets (head,level,point,xy) | logits (head, level*point)]
 //   out  [Nq, 256] T  = sum_{visible cams} MSDA_cam(q) / max(1, #visible cams)
 //   hits (optional) [Nq] u8 = #visible cams (for tests / statistics)
-template <typename T, int MINB>
-__global__ void __launch_bounds__(256, MINB)
+template <typename T>
+__global__ void __launch_bounds__(256, 3)
 sca_fused_kernel(const T* __restrict__ value, const float* __restrict__ qproj, ScaParams sp, LevelGeom lg,
-                 int Nv, T* __restrict__ out, uint8_t* __restrict__ hits, int tile_mode)
+                 int Nv, T* __restrict__ out, uint8_t* __restrict__ hits)
 {
     const int Nq = sp.bev_h * sp.bev_w;
-    int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (tile_mode) {                                             // CTA = 4 (x) x 2 (y) BEV tile: neighbouring pillars
-        const int tiles_x = sp.bev_w >> 2, w = threadIdx.x >> 5; // project to neighbouring pixels in every camera
-        q = ((blockIdx.x / tiles_x) * 2 + (w >> 2)) * sp.bev_w + (blockIdx.x % tiles_x) * 4 + (w & 3);
-    }
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= Nq) return;
     const int lane = threadIdx.x & 31, head = lane >> 2, s = lane & 3;   // s doubles as the owned level
     const unsigned FULL = 0xffffffffu;
@@ -449,37 +621,56 @@ int launch_msda_forward(const float* value, const int64_t* shapes, const int64_t
 }
 
 template <typename T>
-int launch_tsa_fused(const T* value_prev, const T* value_cur, const float* qproj, int bev_h, int bev_w, T* out,
+int launch_tsa_fused(const T* value_prev, const T* value_cur, const void* qproj, bool q_half, int bev_h, int bev_w, T* out,
                      cudaStream_t stream)
 {
     OCC_CHECK(bev_h >= 2 && bev_w >= 2, "tsa_fused: the BEV grid must be at least 2x2");
     const int Nq = bev_h * bev_w;
-    tsa_fused_kernel<T><<<ceil_div(Nq, 8), 256, 0, stream>>>(value_prev, value_cur, qproj, bev_h, bev_w, out);
+    const dim3 grid(ceil_div(Nq, 8));
+    if (q_half) tsa_fused_kernel<T, __half><<<grid, 256, 0, stream>>>(value_prev, value_cur, (const __half*)qproj, bev_h, bev_w, out);
+    else        tsa_fused_kernel<T, float><<<grid, 256, 0, stream>>>(value_prev, value_cur, (const float*)qproj, bev_h, bev_w, out);
     OCC_CUDA(cudaGetLastError());
     return 0;
 }
-template int launch_tsa_fused<float>(const float*, const float*, const float*, int, int, float*, cudaStream_t);
-template int launch_tsa_fused<bf16>(const bf16*, const bf16*, const float*, int, int, bf16*, cudaStream_t);
+template int launch_tsa_fused<float>(const float*, const float*, const void*, bool, int, int, float*, cudaStream_t);
+template int launch_tsa_fused<bf16>(const bf16*, const bf16*, const void*, bool, int, int, bf16*, cudaStream_t);
 
 template <typename T>
-int launch_sca_fused(const T* value, const float* qproj, const ScaParams& sp, const LevelGeom& lg, int Nv, T* out,
-                     uint8_t* hits, cudaStream_t stream)
+int launch_sca_fused(const T* value, const void* qproj_v, bool q_half, const ScaParams& sp, const LevelGeom& lg, int Nv,
+                     T* out, uint8_t* hits, cudaStream_t stream)
 {
     OCC_CHECK(lg.num_levels == 4 && sp.num_cams <= 8 && sp.D <= 8 && sp.D >= 1 && 8 % sp.D == 0,
               "sca_fused: supports 4 levels, <= 8 cameras, pillar anchors in {1,2,4,8}");
     for (int l = 0; l < 4; ++l) OCC_CHECK(lg.h[l] >= 2 && lg.w[l] >= 2, "sca_fused: every level must be at least 2x2");
     const int Nq = sp.bev_h * sp.bev_w;
-    static const int minb = getenv("OCC_SCA_MINB") ? atoi(getenv("OCC_SCA_MINB")) : 3;   // tuning knob (registers vs occupancy)
-    static const int tile_env = getenv("OCC_SCA_TILE") ? atoi(getenv("OCC_SCA_TILE")) : 0;
-    const int tile_mode = (tile_env && sp.bev_w % 4 == 0 && sp.bev_h % 2 == 0) ? 1 : 0;
-    if (minb == 2) sca_fused_kernel<T, 2><<<ceil_div(Nq, 8), 256, 0, stream>>>(value, qproj, sp, lg, Nv, out, hits, tile_mode);
-    else           sca_fused_kernel<T, 3><<<ceil_div(Nq, 8), 256, 0, stream>>>(value, qproj, sp, lg, Nv, out, hits, tile_mode);
+    const dim3 grid(ceil_div(Nq, 8));
+    if constexpr (sizeof(T) == 2) {
+        // production bf16 kernel: descriptor-staged gather, 4 warps per CTA, 6 CTAs per SM (OCC_SCA_PIPE=0: the
+        // shuffle-broadcast kernel that is also the fp32 path; measured variants: profiles/README.md)
+        static const int pipe = getenv("OCC_SCA_PIPE") ? atoi(getenv("OCC_SCA_PIPE")) : 416;
+        bool done = true;
+#define OCC_SCA_CASE(W, D, B)                                                                                       \
+    case 100 * W + 10 * D + B:                                                                                      \
+        if (q_half) sca_pipe_kernel<__half, D, B, W><<<ceil_div(Nq, W), W * 32, 0, stream>>>(value, (const __half*)qproj_v, sp, lg, Nv, out, hits); \
+        else        sca_pipe_kernel<float, D, B, W><<<ceil_div(Nq, W), W * 32, 0, stream>>>(value, (const float*)qproj_v, sp, lg, Nv, out, hits);  \
+        break;
+        switch (pipe) {
+        OCC_SCA_CASE(4, 1, 6)
+        OCC_SCA_CASE(8, 1, 3)
+        default: done = false;
+        }
+#undef OCC_SCA_CASE
+        if (done) { OCC_CUDA(cudaGetLastError()); return 0; }
+    }
+    OCC_CHECK(!q_half, "sca_fused: the unpipelined kernel reads fp32 projections");
+    const float* qproj = (const float*)qproj_v;
+    sca_fused_kernel<T><<<grid, 256, 0, stream>>>(value, qproj, sp, lg, Nv, out, hits);
     OCC_CUDA(cudaGetLastError());
     return 0;
 }
-template int launch_sca_fused<float>(const float*, const float*, const ScaParams&, const LevelGeom&, int, float*,
+template int launch_sca_fused<float>(const float*, const void*, bool, const ScaParams&, const LevelGeom&, int, float*,
                                      uint8_t*, cudaStream_t);
-template int launch_sca_fused<bf16>(const bf16*, const float*, const ScaParams&, const LevelGeom&, int, bf16*,
+template int launch_sca_fused<bf16>(const bf16*, const void*, bool, const ScaParams&, const LevelGeom&, int, bf16*,
                                     uint8_t*, cudaStream_t);
 
 int launch_project_pillars(const ScaParams& sp, float* ref_cam, uint8_t* mask, cudaStream_t stream)
