@@ -62,8 +62,11 @@ namespace {
 
 constexpr int BLOCK_M = 128, BLOCK_K = 64, A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int NUM_THREADS = 320;                          // TMA warp, MMA warp, 8 epilogue warps
-constexpr int SMEM_TAIL = 256 + 2048 + 8 * 4096;          // barriers, LN partials, 8 staging blocks
-constexpr int SMEM_LIMIT = 232448 - 1024 - SMEM_TAIL;          // 227 KB opt-in maximum minus alignment slack and barriers
+// shared-memory tail after the operand ring: 8 per-warp staging blocks (4 KB each; 2 KB when a 16-bit output leaves
+// through 32-column TMA stores), 256 B of barriers, 2 KB of LayerNorm partials (LN kernels only)
+//   + the CTA's per-column constants (bias; gamma, beta for LN) as fp32: 1 KB / 3 KB
+constexpr int smem_tail(bool ln, int stg_bytes) { return 8 * stg_bytes + 256 + (ln ? 2048 + 3072 : 1024); }
+constexpr int SMEM_MAX = 232448 - 1024;                   // 227 KB opt-in maximum minus alignment slack
 constexpr int MAX_STAGES = 6;
 
 struct LnArgs {                                           // fused LayerNorm epilogue (N == BN == 256)
@@ -76,7 +79,9 @@ struct LnArgs {                                           // fused LayerNorm epi
 template <typename TC, bool LN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)          // 10 warps -> 3 on one SMSP -> <= 168 regs (16K per SMSP)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-               const __grid_constant__ CUtensorMap tmW, const float* __restrict__ bias,
+               const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmC,
+               int c_tma /* 0: none, 1: [M,N] row-major, 2: n-blocks as separate [M,BN] matrices */, int stg_bytes,
+               const float* __restrict__ bias,
                const float* __restrict__ residual, TC* __restrict__ C, LnArgs ln, int M, int N, int BN, int nk,
                int nk1, int act, int w_resident, int stages, long long ldc, long long nblk_stride,
                long long* __restrict__ dbg)
@@ -100,7 +105,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t w_region = w_resident ? nk * w_tile_bytes : 0;
     const uint32_t stage_bytes = A_TILE_BYTES + (w_resident ? 0 : w_tile_bytes);
     const uint32_t ring_base = smem_base + w_region;
-    const uint32_t bar_base = ring_base + stages * stage_bytes;
+    const uint32_t stg_base = ring_base + stages * stage_bytes;  // 8 x 4 KB epilogue staging blocks (1024-byte aligned: TMA swizzle)
+    const uint32_t bar_base = stg_base + 8 * stg_bytes;
     auto full_bar = [&](int s) { return bar_base + s * 8; };
     auto empty_bar = [&](int s) { return bar_base + (MAX_STAGES + s) * 8; };
     auto tfull_bar = [&](int s) { return bar_base + (2 * MAX_STAGES + s) * 8; };
@@ -122,12 +128,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmA); tc::tma_prefetch_desc(&tmA2); tc::tma_prefetch_desc(&tmW);
+        if (c_tma) tc::tma_prefetch_desc(&tmC);
         for (int s = 0; s < stages; ++s) { tc::mbar_init(full_bar(s), 1); tc::mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < 2; ++s) { tc::mbar_init(tfull_bar(s), 1); tc::mbar_init(tempty_bar(s), 256); }
         tc::mbar_init(w_bar, 1);
         tc::mbar_fence_init();
     }
     if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+    // Per-column constants of this CTA's n-block -> shared memory, once.  (Parameters: no dependency on the previous
+    // grid.)  Reading them with __ldg inside the epilogue loop exposed one L2 round trip per 32-column chunk -- the
+    // streaming residual / output traffic evicts them from L1 between tiles -- which was most of the epilogue time.
+    float* const cvec = reinterpret_cast<float*>(smem_raw + (bar_base + 256 + (LN ? 2048 : 0) - tc::smem_u32(smem_raw)));
+    if (threadIdx.x >= 64) {
+        const int t = threadIdx.x - 64;                          // 0..255
+        if (t < BN) {
+            cvec[t] = bias ? __ldg(bias + (blockIdx.x % (N / BN)) * BN + t) : 0.f;
+            if constexpr (LN) { cvec[256 + t] = __ldg(ln.gamma + t); cvec[512 + t] = __ldg(ln.beta + t); }
+        }
+    }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -196,7 +214,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ew = warp - 2;
         const int ncol = BN >> 1;                                // columns owned by this warp
         const int cbeg = half * ncol;
-        const uint32_t stg = bar_base + 256 + 2048 + ew * 4096;  // this warp's staging block (shared address)
+        const uint32_t stg = stg_base + ew * stg_bytes;          // this warp's staging block (shared address)
         float2* part = reinterpret_cast<float2*>(smem_raw + (bar_base + 256 - tc::smem_u32(smem_raw)));   // [2][128]
         const int crow = lane >> 3, cpiece = lane & 7;           // coalesced shape: row 4*i + crow, 16-byte piece cpiece
         // plain C++ accesses through a generic pointer (not volatile asm) so the compiler may overlap the
@@ -242,7 +260,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 __syncwarp();
             };
             if constexpr (!LN) {
-                fetch(residual, N, n_blk * BN + cbeg);           // independent of the MMA: issue before waiting on it
+                if (!(sizeof(TC) == 2 && c_tma != 0))
+                    fetch(residual, N, n_blk * BN + cbeg);       // independent of the MMA: issue before waiting on it
                 tc::mbar_wait(tfull_bar(as), aph);
                 if (warp == 2 && lane == 0 && etile < 3) stamp(4 + etile * 3);      // accumulator ready
                 tc::tc_fence_after();
@@ -276,7 +295,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tc::tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0) + i);
+                        const float4 b = reinterpret_cast<const float4*>(cvec + c0)[i];
                         const float x0 = __uint_as_float(r[4 * i]) + b.x + q[i].x, x1 = __uint_as_float(r[4 * i + 1]) + b.y + q[i].y;
                         const float x2 = __uint_as_float(r[4 * i + 2]) + b.z + q[i].z, x3 = __uint_as_float(r[4 * i + 3]) + b.w + q[i].w;
                         sum += (x0 + x1) + (x2 + x3);
@@ -304,8 +323,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     float4* yo = reinterpret_cast<float4*>(ln.y_f32) + blk4 + (size_t)(c0 >> 5) * 256;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {                // normalise my row: fp32 straight to T32, bf16 via staging
-                        const float4 g = __ldg(reinterpret_cast<const float4*>(ln.gamma + c0) + j);
-                        const float4 be = __ldg(reinterpret_cast<const float4*>(ln.beta + c0) + j);
+                        const float4 g = reinterpret_cast<const float4*>(cvec + 256 + c0)[j];
+                        const float4 be = reinterpret_cast<const float4*>(cvec + 512 + c0)[j];
                         float4 y;
                         y.x = (__uint_as_float(r[4 * j]) - mean) * rstd * g.x + be.x;
                         y.y = (__uint_as_float(r[4 * j + 1]) - mean) * rstd * g.y + be.y;
@@ -340,6 +359,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     __syncwarp();
                 }
+            } else if (sizeof(TC) == 2 && c_tma != 0) {
+                // 16-bit outputs: accumulator row -> bias/act -> packed 16-bit -> swizzled staging rows -> ONE TMA store
+                // per [32 rows x box] block.  No shared-memory read-back, no per-lane global stores: the LSU only sees
+                // the 16-byte STS of each thread's own row (conflict-free under the TMA swizzle).
+                const int box = stg_bytes >= 4096 && (ncol & 63) == 0 ? 64 : 32;   // columns per store (= tensor map box)
+                for (int c0 = cbeg; c0 < cbeg + ncol; c0 += box) {
+                    const int col = n_blk * BN + c0;
+                    uint32_t r[64];
+                    {
+                        uint32_t (&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+                        uint32_t (&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
+                        tc::tmem_ld32(taddr + c0, lo);
+                        if (box == 64) tc::tmem_ld32(taddr + c0 + 32, hi);
+                        tc::tmem_ld_wait();
+                    }
+                    uint32_t pk[32];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {               // 4 columns per step (bias is warp-uniform: broadcast loads)
+                        if (4 * j < box) {
+                            const float4 b4 = reinterpret_cast<const float4*>(cvec + c0)[j];
+                            float x0 = __uint_as_float(r[4 * j]) + b4.x, x1 = __uint_as_float(r[4 * j + 1]) + b4.y;
+                            float x2 = __uint_as_float(r[4 * j + 2]) + b4.z, x3 = __uint_as_float(r[4 * j + 3]) + b4.w;
+                            if (act == ACT_RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+                            if constexpr (std::is_same<TC, __half>::value) {
+                                const __half2 a = __floats2half2_rn(x0, x1), b = __floats2half2_rn(x2, x3);
+                                pk[2 * j] = *reinterpret_cast<const uint32_t*>(&a); pk[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&b);
+                            } else {
+                                pk[2 * j] = pack_bf16x2(x0, x1); pk[2 * j + 1] = pack_bf16x2(x2, x3);
+                            }
+                        }
+                    }
+                    if (lane == 0) tc::tma_store_wait_read();    // the previous store has drained the staging block
+                    __syncwarp();
+                    if (box == 64) {                             // 128-byte rows, SWIZZLE_128B: piece j -> j ^ (row & 7)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 128 + ((j ^ (lane & 7)) << 4)),
+                                         "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
+                    } else {                                     // 64-byte rows, SWIZZLE_64B: piece j -> j ^ ((row >> 1) & 3)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)),
+                                         "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
+                    }
+                    tc::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (c_tma == 2) tc::tma_store_3d(&tmC, stg, c0, row0, n_blk);
+                        else            tc::tma_store_3d(&tmC, stg, col, row0, 0);
+                        tc::tma_store_commit();
+                    }
+                }
             } else {
                 const int nchunk = ncol >> 5;                    // BN/2 is a multiple of 32 for every plan (<= 4 chunks)
 #pragma unroll
@@ -355,8 +426,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         sts4(lane, j, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
                     __syncwarp();
-                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + col) + cpiece);
+                    const float4 b4 = reinterpret_cast<const float4*>(cvec + c0)[cpiece];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {                // bias / act / residual / store in the coalesced shape
                         const int rr = 4 * i + crow, grow = row0 + rr;
@@ -391,6 +461,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (++as == 2) { as = 0; aph ^= 1; }
         }
     }
+    if (c_tma != 0 && warp >= 2 && lane == 0) tc::tma_store_wait_all();   // output stores performed before the grid completes
     tc::tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) stamp(15);
@@ -403,8 +474,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // tile-N choice: prefer a weight block that fits resident (<= 128 KB) next to >= 4 A stages
 struct Plan { int BN, resident, stages, smem; };
 
-Plan make_plan(int N, int K, bool ln)
+Plan make_plan(int N, int K, bool ln, int stg_bytes = 4096)
 {
+    const int SMEM_TAIL = smem_tail(ln, stg_bytes), SMEM_LIMIT = SMEM_MAX - SMEM_TAIL;
     Plan p{0, 0, 0, 0};
     const int cands[] = {256, 192, 128, 64};                  // BN/2 must be a multiple of 32 (epilogue column split)
     if (ln) {
@@ -454,18 +526,55 @@ int cached_map_2d(const void* base, uint64_t inner, uint64_t rows, uint32_t box_
     return 0;
 }
 
+// output tensor map for the TMA-store epilogue: dims {cols, rows, blocks}, 2-byte elements, box {box_cols, 32, 1}
+int cached_map_out(const void* base, uint64_t cols, uint64_t rows, uint64_t blocks, uint32_t box_cols, CUtensorMap* out)
+{
+    static std::map<std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t>, CUtensorMap> cache;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> g(mu);
+    const auto k = std::make_tuple(base, cols, rows, blocks, box_cols);
+    auto it = cache.find(k);
+    if (it == cache.end()) {
+        CUtensorMap m;
+        const uint64_t dims[3] = {cols, rows, blocks}, strides[2] = {cols * 2, rows * cols * 2};
+        const uint32_t box[3] = {box_cols, 32, 1};
+        if (make_tensor_map_bf16(&m, base, 3, dims, strides, box, (int)box_cols * 2)) return 1;
+        if (cache.size() > 4096) cache.clear();
+        it = cache.emplace(k, m).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
 template <typename TC, bool LN>
 int launch(const bf16* A, const bf16* A2, int K1, const bf16* W, const float* bias, const float* residual, TC* C,
            LnArgs ln, int M, int N, int K, int act, cudaStream_t stream, bool blocked_out = false)
 {
     if (A2 == nullptr) K1 = K;
-    const Plan p = make_plan(N, K, LN);
+    // 16-bit outputs without a residual leave through TMA stores of [32 rows x 32 columns] (OCC_GEMM_NO_TMA_STORE=1:
+    // per-lane stores): a 2 KB staging block per warp instead of 4 KB, which buys one or two more operand stages
+    static const bool no_tma_store = getenv("OCC_GEMM_NO_TMA_STORE") != nullptr;
+    const bool use_tma_store = !LN && sizeof(TC) == 2 && residual == nullptr && C != nullptr && !no_tma_store;
+    const int stg_bytes = use_tma_store ? 2048 : 4096;
+    const Plan p = make_plan(N, K, LN, stg_bytes);
     OCC_CHECK(p.BN > 0 && p.stages >= 2 && K % 64 == 0 && K1 % 64 == 0 && M > 0, "gemm_tc: unsupported shape");
     CUtensorMap tmA, tmA2, tmW;
     if (cached_map_2d(A, (uint64_t)K1, (uint64_t)M, BLOCK_K, BLOCK_M, &tmA)) return 1;
     if (A2) { if (cached_map_2d(A2, (uint64_t)(K - K1), (uint64_t)M, BLOCK_K, BLOCK_M, &tmA2)) return 1; }
     else tmA2 = tmA;
     if (cached_map_2d(W, (uint64_t)K, (uint64_t)N, BLOCK_K, (uint32_t)p.BN, &tmW)) return 1;
+    CUtensorMap tmC = tmW;
+    int c_tma = 0;
+    if (use_tma_store) {
+        const uint32_t box_cols = 32u;
+        if (blocked_out) {
+            if (cached_map_out(C, (uint64_t)p.BN, (uint64_t)M, (uint64_t)(N / p.BN), box_cols, &tmC)) return 1;
+            c_tma = 2;
+        } else {
+            if (cached_map_out(C, (uint64_t)N, (uint64_t)M, 1, box_cols, &tmC)) return 1;
+            c_tma = 1;
+        }
+    }
     static int num_sms = 0;
     if (num_sms == 0) {
         int dev = 0;
@@ -497,7 +606,7 @@ int launch(const bf16* A, const bf16* A2, int K1, const bf16* W, const float* bi
         const int nk = K / BLOCK_K, nk1 = K1 / BLOCK_K, res = p.resident, stg = p.stages;
         const long long ldc = blocked_out ? (long long)p.BN : (long long)N;
         const long long nbs = blocked_out ? (long long)M * p.BN : (long long)p.BN;
-        OCC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<TC, LN>, tmA, tmA2, tmW, bias, residual, C, ln, M, N, p.BN, nk, nk1,
+        OCC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<TC, LN>, tmA, tmA2, tmW, tmC, c_tma, stg_bytes, bias, residual, C, ln, M, N, p.BN, nk, nk1,
                                     act, res, stg, ldc, nbs, dbg));
     }
     OCC_CUDA(cudaGetLastError());
