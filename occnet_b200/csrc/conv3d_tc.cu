@@ -9,7 +9,7 @@
 // in the coordinates; out-of-bounds rows are zero-filled by the TMA unit, which IS the conv's zero padding
 // (including the z = -1 / z = 16 halo).  All 27 weight tiles stay resident in shared memory.
 //   warp 0: TMA producer (8-stage ring)    warp 1: tcgen05.mma issuer (plane-major: each loaded tile feeds the
-//   dx = 0/1/2 taps of three neighbouring outputs, whose accumulators live in 4 TMEM slots)
+//   dx = 0/1/2 taps of three neighbouring outputs through ONE N = 96 MMA into adjacent TMEM slots, ring of 8)
 //   warps 2-5: epilogue (tcgen05.ld -> +bias -> ReLU -> bf16 -> 64-byte rows, contiguous 8 KB per tile)
 #include "common.cuh"
 #include "conv3d_tc.cuh"
@@ -19,14 +19,20 @@ namespace occ {
 
 namespace {
 
-constexpr int STAGES = 8, TILE_Y = 8, TILE_Z = 16, BLOCK_M = 128, COUT = 32, TAPS = 27, SLOTS = 4;
+constexpr int STAGES = 8, TILE_Y = 8, TILE_Z = 16, BLOCK_M = 128, COUT = 32, TAPS = 27, SLOTS = 8;
 constexpr int NUM_THREADS = 192;
+constexpr int BAR_BYTES = 512;
 
 // Plane-major schedule: an input tile (plane x = p, shift (dz,dy)) is the A operand of three taps -- dx = 0, 1, 2 of
-// the outputs x = p+1, p, p-1 -- so it is loaded ONCE and multiplied into three live accumulators (4 TMEM slots of
-// 32 columns).  L2->SMEM traffic drops from 27 to ~9 tile loads per output tile.  Each CTA owns a contiguous range
-// of the (y_tile, x) tile sequence, cut into segments of constant y_tile; a segment [xa, xb) streams the planes
-// max(xa-1,0) .. min(xb, X-1).
+// the outputs x = p+1, p, p-1 -- so it is loaded ONCE (L2->SMEM traffic: ~9 instead of 27 tile loads per output tile)
+// and multiplied into the three live accumulators with ONE tcgen05.mma of N = 96: the accumulators of consecutive
+// outputs sit in consecutive 32-column TMEM slots (ring of 8), and the weight tiles of a (dz,dy) pair are resident in
+// the order dx = 2, 1, 0, i.e. ascending output x.  (The first version issued three N = 32 MMAs per tile: ncu showed
+// the single MMA-issuing thread, not TMA or the tensor pipe, was the limiter -- ~64 pipe cycles and ~180 issue-thread
+// cycles per tiny MMA.)  Accumulators are zeroed by the epilogue warps when they drain a slot, so every MMA
+// accumulates and the issue loop has no per-output special cases.
+// Each CTA owns a contiguous range of the (y_tile, x) tile sequence, cut into segments of constant y_tile; a segment
+// [xa, xb) streams the planes max(xa-1,0) .. min(xb, X-1).
 template <int CIN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
@@ -69,7 +75,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
     if (warp == 0) {
         if (lane == 0) {
             tc::mbar_arrive_expect_tx(w_bar, TAPS * W_TAP_BYTES);
-            for (int t = 0; t < TAPS; ++t) tc::tma_load_2d(w_base + t * W_TAP_BYTES, &tmW, w_bar, 0, t * COUT);
+            for (int t = 0; t < TAPS; ++t)                   // global tap order is (dz,dy,dx); resident order (dz,dy,2-dx)
+                tc::tma_load_2d(w_base + ((t / 3) * 3 + (2 - t % 3)) * W_TAP_BYTES, &tmW, w_bar, 0, t * COUT);
             int s = 0; uint32_t ph = 0;
             for (int t = t_begin; t < t_end;) {
                 const int yt = t / X, xa = t % X;
@@ -90,7 +97,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = tc::make_idesc_bf16(BLOCK_M, COUT);
+            const uint32_t idesc1 = tc::make_idesc_bf16(BLOCK_M, COUT), idesc2 = tc::make_idesc_bf16(BLOCK_M, 2 * COUT),
+                           idesc3 = tc::make_idesc_bf16(BLOCK_M, 3 * COUT);
+            auto idesc_of = [&](int outputs) { return outputs == 1 ? idesc1 : (outputs == 2 ? idesc2 : idesc3); };
+            const uint64_t da0 = tc::make_smem_desc(a_base, ROW_BYTES), db0 = tc::make_smem_desc(w_base, ROW_BYTES);
             int s = 0; uint32_t ph = 0;
             int n_base = 0;
             tc::mbar_wait(w_bar, 0);
@@ -100,28 +110,37 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
                 const int xb = min(X, xa + (t_end - t));
                 const int p_lo = max(xa - 1, 0), p_hi = min(xb, X - 1);
                 for (int p = p_lo; p <= p_hi; ++p) {
+                    const int x_lo = max(p - 1, xa), x_hi = min(p + 1, xb - 1);      // outputs this plane feeds
+                    const int cnt = x_hi - x_lo + 1, off = x_lo - (p - 1);            // 1..3 outputs, first weight sub-tile
+                    const int n_lo = n_base + (x_lo - xa), slot_lo = n_lo & (SLOTS - 1);
+                    const int first = min(cnt, SLOTS - slot_lo);                       // outputs before the ring wraps
+                    // outputs whose first plane this is: x = p+1 (and x = 0 on plane 0) -- their slot must be drained + zeroed
+                    for (int x = x_lo; x <= x_hi; ++x) {
+                        if (max(x - 1, 0) != p) continue;
+                        const int n = n_base + (x - xa);
+                        tc::mbar_wait(tempty_bar(n & (SLOTS - 1)), (n / SLOTS) & 1);
+                    }
+                    tc::tc_fence_after();
+                    const uint32_t d0 = tmem_base + slot_lo * COUT;
+                    const uint32_t i_first = idesc_of(first), i_rest = idesc_of(cnt - first);
                     for (int t9 = 0; t9 < 9; ++t9) {
                         tc::mbar_wait(full_bar(s), ph);
                         tc::tc_fence_after();
-                        const uint64_t da = tc::make_smem_desc(a_base + s * A_BYTES, ROW_BYTES);
+                        const uint64_t da = da0 + (uint64_t)((s * A_BYTES) >> 4);
+                        const uint64_t db = db0 + (uint64_t)(((t9 * 3 + off) * W_TAP_BYTES) >> 4);
 #pragma unroll
-                        for (int dx = 0; dx < 3; ++dx) {
-                            const int x = p - dx + 1;                       // the output this tile feeds through tap dx
-                            if (x < xa || x >= xb) continue;
-                            const int n = n_base + (x - xa), slot = n & (SLOTS - 1);
-                            const bool opens = (t9 == 0) && (p == max(x - 1, 0));
-                            if (opens) {                                    // accumulator slot must have been drained
-                                tc::mbar_wait(tempty_bar(slot), ((n / SLOTS) & 1) ^ 1);
-                                tc::tc_fence_after();
-                            }
-                            const uint64_t db = tc::make_smem_desc(w_base + (t9 * 3 + dx) * W_TAP_BYTES, ROW_BYTES);
-#pragma unroll
-                            for (int k = 0; k < CIN / 16; ++k)
-                                tc::umma_bf16(tmem_base + slot * 32, da + 2 * k, db + 2 * k, idesc, !(opens && k == 0));
-                            if (t9 == 8 && p == min(x + 1, X - 1)) tc::umma_commit(tfull_bar(slot));   // output complete
+                        for (int k = 0; k < CIN / 16; ++k) {
+                            tc::umma_bf16(d0, da + 2 * k, db + 2 * k, i_first, 1);
+                            if (first < cnt)
+                                tc::umma_bf16(tmem_base, da + 2 * k, db + (uint64_t)((first * W_TAP_BYTES) >> 4) + 2 * k, i_rest, 1);
                         }
                         tc::umma_commit(empty_bar(s));
                         if (++s == STAGES) { s = 0; ph ^= 1; }
+                    }
+                    // outputs whose last plane this was: x = p-1 (and x = X-1 on the last plane)
+                    for (int x = x_lo; x <= x_hi; ++x) {
+                        if (min(x + 1, X - 1) != p) continue;
+                        tc::umma_commit(tfull_bar((n_base + (x - xa)) & (SLOTS - 1)));
                     }
                 }
                 n_base += xb - xa;
@@ -130,6 +149,16 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
         }
     } else {
         const int quarter = warp & 3;
+        const uint32_t tq = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        uint32_t zero[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) zero[i] = 0u;
+#pragma unroll
+        for (int sl = 0; sl < SLOTS; ++sl) tc::tmem_st32(tq + sl * COUT, zero);      // all accumulators start at zero
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+#pragma unroll
+        for (int sl = 0; sl < SLOTS; ++sl) tc::mbar_arrive(tempty_bar(sl));
         float b[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) b[i] = __ldg(bias + i);
@@ -140,10 +169,12 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
             tc::mbar_wait(tfull_bar(slot), (n / SLOTS) & 1);
             tc::tc_fence_after();
             uint32_t r[32];
-            tc::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * 32, r);
+            tc::tmem_ld32(tq + slot * COUT, r);
             tc::tmem_ld_wait();
+            tc::tmem_st32(tq + slot * COUT, zero);           // accumulator is in registers: re-zero and release the slot
+            tc::tmem_st_wait();
             tc::tc_fence_before();
-            tc::mbar_arrive(tempty_bar(slot));               // accumulator is in registers: release TMEM early
+            tc::mbar_arrive(tempty_bar(slot));
             const int row = quarter * 32 + lane;
             const int y = y0 + row / TILE_Z, z = row % TILE_Z;
             if (y < Y) {
@@ -190,7 +221,7 @@ int launch_conv3d_tc(const bf16* in, const bf16* w_tap_major, const float* bias,
         if (make_tensor_map_bf16(&tmW, w_tap_major, 2, dims, strides, box, row_bytes)) return 1;
     }
     const int a_bytes = BLOCK_M * row_bytes, w_bytes = (TAPS * COUT * row_bytes + 1023) & ~1023;
-    const int smem = 1024 + w_bytes + STAGES * a_bytes + 256;
+    const int smem = 1024 + w_bytes + STAGES * a_bytes + BAR_BYTES;
     static int num_sms = 0;
     if (num_sms == 0) {
         int dev = 0;

@@ -111,7 +111,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto empty_bar = [&](int s) { return bar_base + (MAX_STAGES + s) * 8; };
     auto tfull_bar = [&](int s) { return bar_base + (2 * MAX_STAGES + s) * 8; };
     auto tempty_bar = [&](int s) { return bar_base + (2 * MAX_STAGES + 2 + s) * 8; };
-    const uint32_t w_bar = bar_base + (2 * MAX_STAGES + 4) * 8;
+    // one barrier per resident weight k-block (the last one collects every block >= 7): the first MMA starts as soon
+    // as ITS 32 KB slice has landed instead of waiting for the whole 128 KB block
+    auto w_bar = [&](int kb) { return bar_base + (2 * MAX_STAGES + 6 + (kb < 7 ? kb : 7)) * 8; };
     const uint32_t tmem_slot = bar_base + (2 * MAX_STAGES + 5) * 8;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -131,21 +133,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (c_tma) tc::tma_prefetch_desc(&tmC);
         for (int s = 0; s < stages; ++s) { tc::mbar_init(full_bar(s), 1); tc::mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < 2; ++s) { tc::mbar_init(tfull_bar(s), 1); tc::mbar_init(tempty_bar(s), 256); }
-        tc::mbar_init(w_bar, 1);
+        for (int kb = 0; kb < 8; ++kb) tc::mbar_init(w_bar(kb), 1);
         tc::mbar_fence_init();
     }
     if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
-    // Per-column constants of this CTA's n-block -> shared memory, once.  (Parameters: no dependency on the previous
-    // grid.)  Reading them with __ldg inside the epilogue loop exposed one L2 round trip per 32-column chunk -- the
-    // streaming residual / output traffic evicts them from L1 between tiles -- which was most of the epilogue time.
     float* const cvec = reinterpret_cast<float*>(smem_raw + (bar_base + 256 + (LN ? 2048 : 0) - tc::smem_u32(smem_raw)));
-    if (threadIdx.x >= 64) {
-        const int t = threadIdx.x - 64;                          // 0..255
-        if (t < BN) {
-            cvec[t] = bias ? __ldg(bias + (blockIdx.x % (N / BN)) * BN + t) : 0.f;
-            if constexpr (LN) { cvec[256 + t] = __ldg(ln.gamma + t); cvec[512 + t] = __ldg(ln.beta + t); }
-        }
-    }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -156,9 +148,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0) {
         if (lane == 0) {
             if (w_resident) {
-                tc::mbar_arrive_expect_tx(w_bar, w_region);
+                for (int kb = 0; kb < nk && kb < 8; ++kb)
+                    tc::mbar_arrive_expect_tx(w_bar(kb), kb < 7 ? w_tile_bytes : (nk - 7) * w_tile_bytes);
                 for (int kb = 0; kb < nk; ++kb)
-                    tc::tma_load_2d(smem_base + kb * w_tile_bytes, &tmW, w_bar, kb * BLOCK_K, n_blk * BN);
+                    tc::tma_load_2d(smem_base + kb * w_tile_bytes, &tmW, w_bar(kb), kb * BLOCK_K, n_blk * BN);
             }
             int s = 0; uint32_t ph = 0;
             asm volatile("griddepcontrol.wait;" ::: "memory");    // A (and residual) come from the previous kernel
@@ -179,13 +172,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             const uint32_t idesc = tc::make_idesc_bf16(BLOCK_M, BN);
             int s = 0; uint32_t ph = 0; int as = 0; uint32_t aph = 0;
-            if (w_resident) { tc::mbar_wait(w_bar, 0); tc::tc_fence_after(); }
-            stamp(2);                                            // weights resident
+            stamp(2);
             int tcount = 0;
             for (int m_row = row_begin; m_row < row_end; m_row += BLOCK_M, ++tcount) {
                 tc::mbar_wait(tempty_bar(as), aph ^ 1);
                 tc::tc_fence_after();
                 for (int kb = 0; kb < nk; ++kb) {
+                    if (w_resident && tcount == 0) tc::mbar_wait(w_bar(kb), 0);      // weight slice kb resident
                     tc::mbar_wait(full_bar(s), ph);
                     if (kb == 0 && tcount < 3) stamp(3 + tcount * 3);    // first A k-block of tile landed
                     tc::tc_fence_after();
@@ -209,6 +202,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // request-rate bound (measured: ~7 us per tile).  So every global access goes through a per-warp 4 KB
         // staging block in shared memory (128-byte rows, 16-byte pieces XOR-swizzled by row) and is issued in the
         // transposed shape: one instruction = 4 rows x 128 contiguous bytes.
+        // Per-column constants of this CTA's n-block -> shared memory, once, by the 8 epilogue warps while the first
+        // tile is loading.  (Parameters: no dependency on the previous grid.)  Reading them with __ldg inside the
+        // epilogue loop exposed one L2 round trip per 32-column chunk -- the streaming residual / output traffic
+        // evicts them from L1 between tiles -- which was most of the epilogue time.
+        {
+            const int t = threadIdx.x - 64;                      // 0..255
+            if (t < BN) {
+                cvec[t] = bias ? __ldg(bias + n_blk * BN + t) : 0.f;
+                if constexpr (LN) { cvec[256 + t] = __ldg(ln.gamma + t); cvec[512 + t] = __ldg(ln.beta + t); }
+            }
+            asm volatile("bar.sync 5, 256;" ::: "memory");
+        }
         const int quarter = warp & 3;
         const int half = (warp - 2) >> 2;
         const int ew = warp - 2;

@@ -10,7 +10,9 @@
 //                                                                                        -> TMEM cols [128,160)
 //   epilogue B: +bias, argmax over the 17 classes, coalesced stores of logits / class / flow via shared memory
 // Two tiles are in flight (TMEM and the hidden buffer are double-buffered): GEMM1 of tile i+1 is issued
-// before GEMM2 of tile i so the tensor pipe overlaps the activation epilogue.
+// before GEMM2 of tile i, and the 8 epilogue warps run epilogue A of tile i+1 BEFORE epilogue B of tile i, so the
+// MUFU-heavy activation pass never waits for GEMM2.  Warp (quarter q, half h) owns TMEM lanes 32q..32q+31 and the
+// hidden columns [32h, 32h+32) (Softplus) + [64+32h, 64+32h+32) (ReLU); the half-0 warps also run epilogue B.
 #include "common.cuh"
 #include "conv3d_tc.cuh"
 #include "tc_common.cuh"
@@ -24,7 +26,7 @@ constexpr int A_BYTES = BLOCK_M * 64;                 // 128 rows x 32 bf16
 constexpr int W1_BYTES = HID * 64;                    // 128 rows x 32 bf16
 constexpr int W2_CHUNK_BYTES = NOUT * 128;            // 32 rows x 64 bf16
 constexpr int H_CHUNK_BYTES = BLOCK_M * 128;          // 128 rows x 64 bf16
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;                     // TMA warp, MMA warp, 8 epilogue warps
 constexpr int MAX_CLS = 19;                           // 17 classes + 2 flow channels live in the 32 GEMM2 columns
 
 // MUFU-based softplus (ex2 / lg2): ~1e-6 relative, far below the bf16 rounding of the hidden activations
@@ -44,7 +46,8 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t a_base = w2_base + 2 * W2_CHUNK_BYTES;                // 4 x 8 KB
     const uint32_t h_base = a_base + A_STAGES * A_BYTES;                 // 2 stages x 2 chunks x 16 KB
     const uint32_t stage_out = h_base + 4 * H_CHUNK_BYTES;               // 4 warps x 32 x 19 floats
-    const uint32_t bar_base = stage_out + 4 * 32 * MAX_CLS * 4 + 64;
+    const uint32_t bias_base = stage_out + 4 * 32 * MAX_CLS * 4;         // 128 + 32 floats: b1cat | b2cat
+    const uint32_t bar_base = bias_base + (HID + NOUT) * 4 + 64;
     auto a_full = [&](int s) { return bar_base + s * 8; };
     auto a_empty = [&](int s) { return bar_base + (A_STAGES + s) * 8; };
     auto h1_full = [&](int s) { return bar_base + (2 * A_STAGES + s) * 8; };      // GEMM1 done
@@ -61,13 +64,18 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc::tma_prefetch_desc(&tmA); tc::tma_prefetch_desc(&tmW1); tc::tma_prefetch_desc(&tmW2);
         for (int s = 0; s < A_STAGES; ++s) { tc::mbar_init(a_full(s), 1); tc::mbar_init(a_empty(s), 1); }
         for (int s = 0; s < 2; ++s) {
-            tc::mbar_init(h1_full(s), 1); tc::mbar_init(h_ready(s), 128);
+            tc::mbar_init(h1_full(s), 1); tc::mbar_init(h_ready(s), 256);
             tc::mbar_init(l_full(s), 1); tc::mbar_init(t_empty(s), 128);
         }
         tc::mbar_init(w_bar, 1);
         tc::mbar_fence_init();
     }
     if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+    float* const sbias = reinterpret_cast<float*>(smem_gen + (bias_base - smem_base));
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + HID + NOUT) {
+        const int t = threadIdx.x - 64;
+        sbias[t] = t < HID ? __ldg(b1cat + t) : (t - HID < ncls + 2 ? __ldg(b2cat + t - HID) : 0.f);
+    }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -128,31 +136,36 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {
-        const int quarter = warp & 3;
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         float* sout = reinterpret_cast<float*>(smem_gen + (stage_out - smem_base)) + quarter * 32 * MAX_CLS;
-        int i = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
+        int n_my = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) ++n_my;
+        // ---- epilogue A of my tile #i: hidden activations -> swizzled bf16 A operand of GEMM2 in shared memory
+        auto epi_a = [&](int i) {
             const int as = i & 1; const uint32_t aph = (i >> 1) & 1;
             const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * 256;
-            // ---- epilogue A: hidden activations -> swizzled bf16 A operand in shared memory
             tc::mbar_wait(h1_full(as), aph);
             tc::tc_fence_after();
 #pragma unroll
-            for (int c0 = 0; c0 < HID; c0 += 32) {
+            for (int part = 0; part < 2; ++part) {
+                const int c0 = part * 64 + half * 32;                     // part 0: Softplus columns, part 1: ReLU columns
                 uint32_t r[32];
                 tc::tmem_ld32(tbase + c0, r);
                 tc::tmem_ld_wait();
-                const uint32_t chunk_base = h_base + (as * 2 + (c0 >> 6)) * H_CHUNK_BYTES + row * 128;
+                const uint32_t chunk_base = h_base + (as * 2 + part) * H_CHUNK_BYTES + row * 128;
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {                             // 4 x 16 bytes = 8 hidden units each
                     float v[8];
+                    const float4 b0 = reinterpret_cast<const float4*>(sbias + c0)[2 * p];
+                    const float4 b1 = reinterpret_cast<const float4*>(sbias + c0)[2 * p + 1];
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const float x = __uint_as_float(r[p * 8 + k]) + __ldg(b1cat + c0 + p * 8 + k);
-                        v[k] = (c0 < 64) ? softplus_f(x) : fmaxf(x, 0.f);
+                        const float x = __uint_as_float(r[p * 8 + k]) + bb[k];
+                        v[k] = (part == 0) ? softplus_f(x) : fmaxf(x, 0.f);
                     }
-                    const int piece = ((c0 & 63) >> 3) + p;               // 16-byte piece index inside the 128 B row
+                    const int piece = half * 4 + p;                       // 16-byte piece index inside the 128 B row
                     const uint32_t addr = chunk_base + ((piece ^ (row & 7)) << 4);
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(v[0], v[1])),
                                  "r"(pack_bf16x2(v[2], v[3])), "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7]))
@@ -162,7 +175,11 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
             tc::tc_fence_before();
             tc::mbar_arrive(h_ready(as));
-            // ---- epilogue B: logits / flow
+        };
+        // ---- epilogue B of my tile #i (half-0 warps): logits / class / flow
+        auto epi_b = [&](int i, int tile) {
+            const int as = i & 1; const uint32_t aph = (i >> 1) & 1;
+            const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * 256;
             tc::mbar_wait(l_full(as), aph);
             tc::tc_fence_after();
             uint32_t r[32];
@@ -174,7 +191,7 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float best = -INFINITY, f0 = 0.f, f1 = 0.f; int arg = 0;
 #pragma unroll
             for (int c = 0; c < MAX_CLS; ++c) {                           // static register indices (no local memory)
-                const float a = __uint_as_float(r[c]) + __ldg(b2cat + (c < ncls + 2 ? c : 0));
+                const float a = __uint_as_float(r[c]) + sbias[HID + c];
                 if (c < ncls) {
                     sout[lane * MAX_CLS + c] = a;
                     if (a > best) { best = a; arg = c; }
@@ -194,6 +211,11 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int j = lane; j < nvalid * ncls; j += 32) dst[j] = sout[(j / ncls) * MAX_CLS + (j % ncls)];
                 __syncwarp();
             }
+        };
+        if (n_my > 0) epi_a(0);
+        for (int i = 0; i < n_my; ++i) {
+            if (i + 1 < n_my) epi_a(i + 1);
+            if (half == 0) epi_b(i, blockIdx.x + i * (int)gridDim.x);
         }
     }
     tc::tc_fence_before();
@@ -228,7 +250,7 @@ int launch_occ_head_tc(const bf16* vox, const bf16* w1cat, const bf16* w2cat, co
         if (make_tensor_map_bf16(&tmW2, w2cat, 2, dims, strides, box, 128)) return 1;
     }
     const int smem = 1024 + W1_BYTES + 2 * W2_CHUNK_BYTES + A_STAGES * A_BYTES + 4 * H_CHUNK_BYTES +
-                     4 * 32 * MAX_CLS * 4 + 64 + 256;
+                     4 * 32 * MAX_CLS * 4 + (HID + NOUT) * 4 + 64 + 256;
     static int num_sms = 0;
     if (num_sms == 0) {
         int dev = 0;

@@ -1,10 +1,8 @@
 cd /root/repo
 rm -f gpurun_out/_sweep_ref.npy gpurun_out/sweep.jsonl gpurun_out/sweep.err
 run() { tag=$1; shift; env "$@" timeout 120 python tests/_sweep_gather.py $tag >> gpurun_out/sweep.jsonl 2>> gpurun_out/sweep.err; }
-run cvec
-run cvec_no_tma OCC_GEMM_NO_TMA_STORE=1
-OCC_GEMM_TIMELINE=1 timeout 120 python tests/_timeline_frame.py 2> gpurun_out/timeline2.log
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/sweep_pytest.log
+run conv96_head8
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/sweep_pytest.log
 cat gpurun_out/sweep.jsonl
 tail -5 gpurun_out/sweep.err
 cat gpurun_out/sweep_pytest.log
