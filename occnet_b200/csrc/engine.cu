@@ -49,6 +49,7 @@ struct LayerW {
     DevBuf ln_g[3], ln_b[3];
     // bf16 copies for the tensor-core path
     DevBuf tsa_v_wh, tsa_q_wh, tsa_o_wh, sca_q_wh, sca_v_wh, sca_o_wh, ffn1_wh, ffn2_wh;
+    DevBuf tsa_q_wh_fold;   // [W1 + W2 | W2]: W1 q + W2 (q + pos) == (W1 + W2) q + W2 pos  (self mode, prev_bev = None)
 };
 
 }  // namespace
@@ -65,6 +66,7 @@ struct occb200_engine {
     std::map<std::string, std::vector<float>> host_params;
     std::vector<LayerW> layers;
     DevBuf bev_queries, pos, pos_t32, cams_embeds, level_embeds;
+    DevBuf pos_bf;                      // bev_pos as a bf16 row-major GEMM operand (folded TSA query projection)
     DevBuf qc_f32, qc_t, qc_pos_t;      // parameter-only layer-0 operands (query fp32 T32, bf16 query, bf16 query+pos), built once
     DevBuf conv_w[2], conv_b[2], conv_wh[2];
     DevBuf sca_v_all_wh, sca_v_all_b, sca_value_all;     // value_proj of every layer, concatenated (tensor-core path)
@@ -78,10 +80,10 @@ struct occb200_engine {
     // pipelined host-buffer variant: 2 slots, copies on their own streams, compute on the caller's stream
     struct Slot {
         DevBuf feats[4], occ, flow;
-        cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
+        cudaEvent_t h2d_done[4] = {nullptr, nullptr, nullptr, nullptr}, compute_done = nullptr, d2h_done = nullptr;
         bool busy = false;
     } slots[2];
-    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaStream_t h2d_stream[4] = {nullptr, nullptr, nullptr, nullptr}, d2h_stream = nullptr;
     int launches = 0;
     // optional per-kernel-category timing (CUDA events on the launch stream)
     bool profiling = false;
@@ -262,7 +264,13 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
             if (gemm<T, T>(e, e->prev_t.as<T>(), nullptr, 0, w.tsa_v_w.as<float>(), w.tsa_v_wh.p,
                            w.tsa_v_b.as<float>(), nullptr, v_prev, Nq, C, C, ACT_NONE, st)) return 2;
         }
-        {
+        // self mode (prev_bev = None): W1 q + W2 (q + pos) = (W1 + W2) q + W2 pos -- the second operand is the CONSTANT
+        // bf16 pos, so no layer has to write (and the FFN LayerNorm epilogue has to read pos for) a bf16 copy of q + pos
+        const bool fold_pos = fuse_ln && !has_prev && w.tsa_q_wh_fold.p != nullptr && e->pos_bf.p != nullptr && q_half;
+        if (fold_pos) {
+            if (gemm<T, __half>(e, q_in, e->pos_bf.as<T>(), C, w.tsa_q_w.as<float>(), w.tsa_q_wh_fold.p, w.tsa_q_b.as<float>(),
+                                nullptr, (__half*)qproj, Nq, nq_tsa, 2 * C, ACT_NONE, st)) return 2;
+        } else {
             const T* qa = has_prev ? e->prev_t.as<T>() : q_in;
             const int rc = q_half ? gemm<T, __half>(e, qa, q_pos_in, C, w.tsa_q_w.as<float>(), w.tsa_q_wh.p, w.tsa_q_b.as<float>(),
                                                     nullptr, (__half*)qproj, Nq, nq_tsa, 2 * C, ACT_NONE, st)
@@ -332,8 +340,10 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
         if (gemm<T, T>(e, q_t, nullptr, 0, w.ffn1_w.as<float>(), w.ffn1_wh.p, w.ffn1_b.as<float>(), nullptr,
                        e->ffn_h.as<T>(), Nq, c.ffn_dim, C, ACT_RELU, st)) return 2;
         if (fuse_ln) {
+            const bool need_qpos = !fold_pos;                // only the unfolded TSA query projection reads q + pos
             if (gemm_ln_fused(e, e->ffn_h.as<bf16>(), w.ffn2_wh.p, w.ffn2_b.as<float>(), q_f32, w.ln_g[2].as<float>(),
-                              w.ln_b[2].as<float>(), e->pos_t32.as<float>(), x_f32, (bf16*)q_t, (bf16*)q_pos_t, Nq, c.ffn_dim, st))
+                              w.ln_b[2].as<float>(), need_qpos ? e->pos_t32.as<float>() : nullptr, x_f32, (bf16*)q_t,
+                              need_qpos ? (bf16*)q_pos_t : nullptr, Nq, c.ffn_dim, st))
                 return 2;
             advance();
         } else {
@@ -474,10 +484,11 @@ void occb200_engine_destroy(occb200_engine* e)
         DevBuf* all[] = {&w.tsa_v_w, &w.tsa_v_b, &w.tsa_q_w, &w.tsa_q_b, &w.tsa_o_w, &w.tsa_o_b, &w.sca_q_w, &w.sca_q_b,
                          &w.sca_v_w, &w.sca_v_b, &w.sca_o_w, &w.sca_o_b, &w.ffn1_w, &w.ffn1_b, &w.ffn2_w, &w.ffn2_b,
                          &w.ln_g[0], &w.ln_g[1], &w.ln_g[2], &w.ln_b[0], &w.ln_b[1], &w.ln_b[2], &w.tsa_v_wh,
-                         &w.tsa_q_wh, &w.tsa_o_wh, &w.sca_q_wh, &w.sca_v_wh, &w.sca_o_wh, &w.ffn1_wh, &w.ffn2_wh};
+                         &w.tsa_q_wh, &w.tsa_o_wh, &w.sca_q_wh, &w.sca_v_wh, &w.sca_o_wh, &w.ffn1_wh, &w.ffn2_wh,
+                         &w.tsa_q_wh_fold};
         for (DevBuf* b : all) b->release();
     }
-    DevBuf* all[] = {&e->qc_f32, &e->qc_t, &e->qc_pos_t, &e->bev_queries, &e->pos, &e->pos_t32, &e->cams_embeds, &e->level_embeds, &e->conv_w[0], &e->conv_w[1],
+    DevBuf* all[] = {&e->pos_bf, &e->qc_f32, &e->qc_t, &e->qc_pos_t, &e->bev_queries, &e->pos, &e->pos_t32, &e->cams_embeds, &e->level_embeds, &e->conv_w[0], &e->conv_w[1],
                      &e->conv_b[0], &e->conv_b[1], &e->conv_wh[0], &e->conv_wh[1], &e->sca_v_all_wh, &e->sca_v_all_b, &e->sca_value_all, &e->hw1, &e->hb1, &e->hw2, &e->hb2,
                      &e->fw1, &e->fb1, &e->fw2, &e->fb2, &e->head_w1h, &e->head_w2h, &e->head_b1c, &e->head_b2c, &e->tokens, &e->sca_value, &e->q_f32, &e->q_t,
                      &e->q_pos_t, &e->q0_t, &e->prev_t, &e->tsa_value, &e->tsa_value_prev, &e->qproj, &e->attn_out,
@@ -488,9 +499,15 @@ void occb200_engine_destroy(occb200_engine* e)
     for (auto& sl : e->slots) {
         for (auto& f : sl.feats) f.release();
         sl.occ.release(); sl.flow.release();
-        if (sl.h2d_done) { cudaEventDestroy(sl.h2d_done); cudaEventDestroy(sl.compute_done); cudaEventDestroy(sl.d2h_done); }
+        if (sl.compute_done) {
+            for (cudaEvent_t ev : sl.h2d_done) cudaEventDestroy(ev);
+            cudaEventDestroy(sl.compute_done); cudaEventDestroy(sl.d2h_done);
+        }
     }
-    if (e->h2d_stream) { cudaStreamDestroy(e->h2d_stream); cudaStreamDestroy(e->d2h_stream); }
+    if (e->d2h_stream) {
+        for (cudaStream_t hs : e->h2d_stream) cudaStreamDestroy(hs);
+        cudaStreamDestroy(e->d2h_stream);
+    }
     for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
     delete e;
 }
@@ -530,6 +547,8 @@ int occb200_engine_finalize(occb200_engine* e)
             if (e->pos_t32.alloc(rows_pad * C * 4)) return 2;
             OCC_CUDA(cudaMemset(e->pos_t32.p, 0, rows_pad * C * 4));
             if (launch_t32_convert(e->pos.as<float>(), e->pos_t32.as<float>(), Nq, 0, 0)) return 2;
+            if (e->pos_bf.alloc((size_t)Nq * C * 2)) return 2;
+            if (launch_cast<bf16>(e->pos.as<float>(), e->pos_bf.as<bf16>(), (int64_t)Nq * C, 0)) return 2;
             // bev_queries / pos are parameters: their fp32 (T32) and bf16 operand forms are frame-independent
             if (e->qc_f32.alloc(rows_pad * C * 4) || e->qc_t.alloc((size_t)Nq * C * 2) || e->qc_pos_t.alloc((size_t)Nq * C * 2))
                 return 2;
@@ -556,7 +575,7 @@ int occb200_engine_finalize(occb200_engine* e)
             return 0;
         };
         auto up_cat = [&](DevBuf& wbuf, DevBuf& bbuf, DevBuf* wh, const std::string& n1, const std::string& n2,
-                          size_t r1, size_t r2, size_t k) -> int {
+                          size_t r1, size_t r2, size_t k, DevBuf* fold = nullptr) -> int {
             const std::vector<float>* W1 = find(e, n1 + ".weight", r1 * k);
             const std::vector<float>* B1 = find(e, n1 + ".bias", r1);
             const std::vector<float>* W2 = find(e, n2 + ".weight", r2 * k);
@@ -567,6 +586,13 @@ int occb200_engine_finalize(occb200_engine* e)
             B.insert(B.end(), B2->begin(), B2->end());
             if (upload(wbuf, W.data(), W.size()) || upload(bbuf, B.data(), B.size())) return 2;
             if (tc && wh && upload_bf16(*wh, W.data(), W.size())) return 2;
+            if (tc && fold) {                                    // k = 2C: fold the first half of every row into (W1 + W2)
+                std::vector<float> Wf(W);
+                const size_t half = k / 2;
+                for (size_t r = 0; r < r1 + r2; ++r)
+                    for (size_t j = 0; j < half; ++j) Wf[r * k + j] = W[r * k + j] + W[r * k + half + j];
+                if (upload_bf16(*fold, Wf.data(), Wf.size())) return 2;
+            }
             return 0;
         };
         int rc;
@@ -574,7 +600,7 @@ int occb200_engine_finalize(occb200_engine* e)
         const size_t sq_off = 8 * c.num_levels * c.sca_points * 2, sq_w = 8 * c.num_levels * c.sca_points;
         if ((rc = up(w.tsa_v_w, w.tsa_v_b, &w.tsa_v_wh, a0 + ".value_proj", C, C))) return rc;
         if ((rc = up_cat(w.tsa_q_w, w.tsa_q_b, &w.tsa_q_wh, a0 + ".sampling_offsets", a0 + ".attention_weights", tq_off,
-                         tq_w, 2 * C))) return rc;
+                         tq_w, 2 * C, &w.tsa_q_wh_fold))) return rc;
         if ((rc = up(w.tsa_o_w, w.tsa_o_b, &w.tsa_o_wh, a0 + ".output_proj", C, C))) return rc;
         if ((rc = up_cat(w.sca_q_w, w.sca_q_b, &w.sca_q_wh, d + ".sampling_offsets", d + ".attention_weights", sq_off,
                          sq_w, C))) return rc;
@@ -745,27 +771,42 @@ int occb200_engine_submit_host(occb200_engine* e, int slot, const float* const* 
     cudaStream_t st = (cudaStream_t)stream;
     occb200_engine::Slot& s = e->slots[slot];
     OCC_CHECK(!s.busy, "slot still in flight: call occb200_engine_wait_host first");
-    if (!e->h2d_stream) {
-        OCC_CUDA(cudaStreamCreateWithFlags(&e->h2d_stream, cudaStreamNonBlocking));
+    if (!e->d2h_stream) {
+        for (cudaStream_t& hs : e->h2d_stream) OCC_CUDA(cudaStreamCreateWithFlags(&hs, cudaStreamNonBlocking));
         OCC_CUDA(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
     }
-    if (!s.h2d_done) {
-        OCC_CUDA(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
+    if (!s.compute_done) {
+        for (cudaEvent_t& ev : s.h2d_done) OCC_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         OCC_CUDA(cudaEventCreateWithFlags(&s.compute_done, cudaEventDisableTiming));
         OCC_CUDA(cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming));
     }
+    // Levels larger than 32 MB go up in `nsplit` pieces on separate copy streams: one cudaMemcpyAsync stream reached
+    // 46 GB/s of the PCIe link on the test box, two reach 50 GB/s (OCC_H2D_SPLIT = 1..4, default 2).
+    static const int nsplit = [] {
+        const char* v = getenv("OCC_H2D_SPLIT");
+        const int n = v ? atoi(v) : 2;
+        return n < 1 ? 1 : (n > 4 ? 4 : n);
+    }();
     const size_t nvox = (size_t)c.bev_w * c.bev_h * c.pillar_h;
     const float* dev_feats[4];
     for (int l = 0; l < 4; ++l) {
         const size_t n = (size_t)c.num_cams * 256 * e->lg.h[l] * e->lg.w[l] * 4;
         if (s.feats[l].bytes != n && s.feats[l].alloc(n)) return 2;
-        OCC_CUDA(cudaMemcpyAsync(s.feats[l].p, feats_host[l], n, cudaMemcpyHostToDevice, e->h2d_stream));
+        const int pieces = n >= (32u << 20) ? nsplit : 1;
+        const size_t chunk = ((n / pieces) + 255) & ~(size_t)255;
+        for (int i = 0; i < pieces; ++i) {
+            const size_t o = (size_t)i * chunk, len = o >= n ? 0 : (n - o < chunk ? n - o : chunk);
+            if (len) OCC_CUDA(cudaMemcpyAsync((char*)s.feats[l].p + o, (const char*)feats_host[l] + o, len,
+                                              cudaMemcpyHostToDevice, e->h2d_stream[i]));
+        }
         dev_feats[l] = s.feats[l].as<float>();
     }
-    OCC_CUDA(cudaEventRecord(s.h2d_done, e->h2d_stream));
+    for (int i = 0; i < nsplit; ++i) {                              // compute waits for this frame's features only
+        OCC_CUDA(cudaEventRecord(s.h2d_done[i], e->h2d_stream[i]));
+        OCC_CUDA(cudaStreamWaitEvent(st, s.h2d_done[i], 0));
+    }
     if (s.occ.bytes != nvox * 8 && s.occ.alloc(nvox * 8)) return 2;
     if (s.flow.bytes != nvox * 8 && s.flow.alloc(nvox * 8)) return 2;
-    OCC_CUDA(cudaStreamWaitEvent(st, s.h2d_done, 0));              // compute waits for this frame's features only
     int rc = occb200_engine_forward(e, dev_feats, nullptr, nullptr, nullptr, s.flow.as<float>(), nullptr,
                                     s.occ.as<int64_t>(), stream);
     if (rc) return rc;
