@@ -1,6 +1,6 @@
 """Turn ncu reports (gpurun_out/*.ncu-rep, scratch) into the small tracked summaries under profiles/.
 
-    python profiles/summarize.py gpurun_out/prof_r1_kernels.ncu-rep gpurun_out/prof_r1_gemm.ncu-rep
+    python profiles/summarize.py gpurun_out/prof_r1_layers.ncu-rep gpurun_out/prof_r1_tail.ncu-rep
 
 Writes profiles/r1_ncu_summary.csv (one row per captured launch) and profiles/r1_traffic.json (DRAM bytes per launch
 and per frame by kernel category, read by bench.py for `roofline.traffic`)."""
@@ -19,9 +19,10 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'smsp__inst_executed.sum', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
         'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct',
-        'sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed']
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed']
 UNIT = {'Mbyte': 1e6, 'Kbyte': 1e3, 'Gbyte': 1e9, 'byte': 1.0, 'us': 1.0, 'ms': 1e3, 'ns': 1e-3, 'msecond': 1e3, 'usecond': 1.0}
-CATEGORY = [('sca_fused', 'sca_gather'), ('tsa_fused', 'tsa_gather'), ('gemm_tc', 'gemm'), ('conv3d_tc', 'conv3d'),
+CATEGORY = [('sca_', 'sca_gather'), ('tsa_fused', 'tsa_gather'), ('gemm_tc', 'gemm'), ('conv3d_tc', 'conv3d'),
             ('head_tc', 'occ_head'), ('pack_level', 'pack')]
 LAUNCHES_PER_FRAME = {'sca_gather': 6, 'tsa_gather': 6, 'conv3d': 2, 'occ_head': 1}
 
