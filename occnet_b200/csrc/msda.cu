@@ -11,10 +11,18 @@
 //        visibility, softmax, Z-anchor interleave, gather, cross-camera sum and /count --
 //        without the reference's nonzero() host sync, rebatch copies and scatter loops.
 //
-// Mapping (both fused kernels): one warp per BEV query; lane = (head = lane/4, slice = lane%4);
+// Mapping (all fused kernels): one warp per BEV query; lane = (head = lane/4, slice = lane%4);
 // a lane accumulates 8 of the head's 32 channels, so one warp-wide 128-bit load instruction
-// fetches 8 independent 64-byte (bf16) corner rows.  Per-sample scalars (location, weight) live
-// in one owner lane per (head, level) and are broadcast inside the 4-lane group with shuffles.
+// fetches 8 independent 64-byte (bf16) corner rows.  Per-sample scalars (location, weight) are
+// prepared by one owner lane per (head, level).
+//   sca_fused_kernel / tsa_fused_kernel (fp32 parity path, bf16 fallback): the owner's packed
+//        sample is broadcast inside the 4-lane group with shuffles.
+//   sca_pipe_kernel (bf16 production path): the owners write 16-byte sample descriptors to shared
+//        memory; the gather loop reads them with one broadcast LDS.128 per sample and issues the
+//        loads of sample i+1 before the FMAs of sample i.  4 warps per CTA, 6 CTAs per SM.
+// Sampling offsets / logits arrive as fp32 or (tensor-core path) fp16.
+// Measured bound (ncu, profiles/README.md): the L1 data path -- every 128-bit warp load touches 6-8
+// different 128-byte lines and replays once per line -- not HBM (11 % dram) or instruction issue (50 %).
 #include <cuda_fp16.h>
 
 #include <cstdlib>
