@@ -109,7 +109,8 @@ int occb200_engine_forward_host(occb200_engine* e, const float* const* feats_hos
                                 float* flow_host, void* stream);
 
 /* Pipelined form of the same call for streams of frames: _submit_host enqueues the host->device copy of the
- * frame's features (copy stream), the frame (caller's stream, after that copy) and the device->host copy of the
+ * frame's features (copy streams; levels above 32 MB are split over OCC_H2D_SPLIT = 1..4 of them, default 2), the
+ * frame (caller's stream, after those copies) and the device->host copy of the
  * results (second copy stream) for `slot` in {0,1} and returns; _wait_host blocks until the slot's results are in
  * the host buffers.  With two slots in flight the copies of frame i+1 / i-1 overlap the compute of frame i.
  * Host buffers must be pinned for the copies to be asynchronous. */
