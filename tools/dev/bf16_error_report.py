@@ -1,6 +1,6 @@
 """Development aid: prints the actual bf16-path errors vs the fp32 oracle (the asserted bounds live in test_gpu_parity.py)."""
 import sys, os, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import test_gpu_parity as t
 O, _, _ = t._oracle()

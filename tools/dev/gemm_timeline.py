@@ -1,5 +1,5 @@
 import torch, os, sys
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from occnet_b200 import _lib
 lib = _lib.load()
 torch.manual_seed(0)

@@ -1,10 +1,10 @@
 """Dev aid (not a test): time one engine configuration (env knobs are read at first launch) and print
 ms/frame + per-category ms, plus max |diff| of occ logits against a reference run saved by the first call.
-  python tests/_sweep_gather.py TAG   (env: OCC_SCA_PIPE, OCC_TSA_DEPTH, OCC_QPROJ_F32, ...)"""
+  python tools/dev/sweep_gather.py TAG   (env: OCC_SCA_PIPE, OCC_TSA_DEPTH, OCC_QPROJ_F32, ...)"""
 import json, os, sys
 import numpy as np
 import torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from occnet_b200 import fixtures
 from occnet_b200.engine import OccEngine
 

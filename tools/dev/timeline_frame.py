@@ -1,7 +1,7 @@
 """Dev aid: one frame with OCC_GEMM_TIMELINE=1 (set by the caller): every tcgen05 GEMM prints its per-CTA timeline."""
 import os, sys
 import torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from occnet_b200 import fixtures
 from occnet_b200.engine import OccEngine
 cfg = fixtures.make_cfg('full', num_layers=2)
