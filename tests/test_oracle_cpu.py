@@ -178,3 +178,68 @@ def test_no_oracle_import_in_product():
             if f.endswith(('.py', '.cu', '.cuh')):
                 src = open(os.path.join(d, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', src, re.M), f'{f} imports the oracle'
+
+
+# ---- image backbone + neck: oracle pinned against torchvision's independent implementations
+def test_backbone_resnet50_matches_torchvision():
+    from torchvision.models import resnet50
+    from oracle import backbone as OB
+    p = OB.init_params(seed=5)
+    m = resnet50(weights=None).eval()
+    sd = {k[len('img_backbone.'):]: v for k, v in p.items() if k.startswith('img_backbone.')}
+    missing = m.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys
+    assert all(k.startswith('fc.') or k.endswith('num_batches_tracked') for k in missing.missing_keys), missing.missing_keys
+    got = {}
+    for name in ('layer2', 'layer3', 'layer4'):
+        getattr(m, name).register_forward_hook(lambda mod, i, o, n=name: got.__setitem__(n, o))
+    img = torch.randn(2, 3, 72, 104, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        m(img)
+        outs = OB.resnet50(p, img)
+    assert [tuple(o.shape) for o in outs] == [(2, 512, 9, 13), (2, 1024, 5, 7), (2, 2048, 3, 4)]
+    for o, name in zip(outs, ('layer2', 'layer3', 'layer4')):
+        assert torch.equal(o, got[name]), (name, (o - got[name]).abs().max())
+
+
+def test_backbone_fpn_matches_torchvision():
+    from collections import OrderedDict
+    from torchvision.ops import FeaturePyramidNetwork
+    from torchvision.ops.feature_pyramid_network import LastLevelP6P7
+    from oracle import backbone as OB
+    p = OB.init_params(seed=6)
+    m = FeaturePyramidNetwork([512, 1024, 2048], 256, extra_blocks=LastLevelP6P7(256, 256)).eval()
+    sd = m.state_dict()
+    for i in range(3):
+        sd[f'inner_blocks.{i}.0.weight'] = p[f'img_neck.lateral_convs.{i}.conv.weight']
+        sd[f'inner_blocks.{i}.0.bias'] = p[f'img_neck.lateral_convs.{i}.conv.bias']
+        sd[f'layer_blocks.{i}.0.weight'] = p[f'img_neck.fpn_convs.{i}.conv.weight']
+        sd[f'layer_blocks.{i}.0.bias'] = p[f'img_neck.fpn_convs.{i}.conv.bias']
+    sd['extra_blocks.p6.weight'] = p['img_neck.fpn_convs.3.conv.weight']
+    sd['extra_blocks.p6.bias'] = p['img_neck.fpn_convs.3.conv.bias']
+    m.load_state_dict(sd)
+    g = torch.Generator().manual_seed(1)
+    feats = [torch.randn(2, 512, 29, 50, generator=g), torch.randn(2, 1024, 15, 25, generator=g),
+             torch.randn(2, 2048, 8, 13, generator=g)]                       # odd sizes: top-down resize is by SIZE
+    with torch.no_grad():
+        ref = m(OrderedDict((str(i), f) for i, f in enumerate(feats)))
+        outs = OB.fpn(p, feats)
+    assert [tuple(o.shape[2:]) for o in outs] == [(29, 50), (15, 25), (8, 13), (4, 7)]
+    for o, k in zip(outs, ('0', '1', '2', 'p6')):
+        assert torch.equal(o, ref[k]), (k, (o - ref[k]).abs().max())
+
+
+def test_backbone_extract_img_feat_shapes():
+    from oracle import backbone as OB
+    p = OB.init_params(seed=5)
+    img = torch.randn(1, 2, 3, 64, 96, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        feats = OB.extract_img_feat(p, img)
+    assert [tuple(f.shape) for f in feats] == [(1, 2, 256, 8, 12), (1, 2, 256, 4, 6), (1, 2, 256, 2, 3), (1, 2, 256, 1, 2)]
+    # the shipped configuration's level shapes (928 x 1600 padded input): strides 8 / 16 / 32 / 64
+    h, w = 928, 1600
+    shapes = []
+    for s in (8, 16, 32):
+        shapes.append((-(-h // s), -(-w // s)))
+    shapes.append((-(-shapes[-1][0] // 2), -(-shapes[-1][1] // 2)))
+    assert shapes == [tuple(s) for s in fixtures.CFG_FULL['level_shapes']]
