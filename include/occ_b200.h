@@ -166,6 +166,27 @@ int occb200_layernorm_f32(const float* x, const float* gamma, const float* beta,
 int occb200_gemm_bf16_tc(const void* A_bf16, const void* W_bf16, const float* bias, float* C, int M, int N, int K,
                          void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Image backbone + neck (the step immediately BEFORE the hot path).  FIRST VERSION: builds for
+ * sm_100a, not yet validated on a GPU (round-1 GPU budget was spent); parity tests are opt-in (OCC_EXPERIMENTAL=1).
+ * Replaces `self.img_backbone(img)` + `self.img_neck(...)` in BEVFormerOcc.extract_img_feat
+ * (detectors/bevformer_occ.py:66-99) for the shipped configuration (bevformer_base_occ.py:48-66): mmdet
+ * ResNet(depth=50, out_indices=(1,2,3), style='pytorch', norm_eval=True) + FPN(in_channels=[512,1024,2048],
+ * out_channels=256, start_level=0, add_extra_convs='on_output', num_outs=4), eval mode.
+ *   precision 0: fp32 storage, CUDA-core GEMMs (parity configuration); 1: bf16 storage (+ tcgen05 GEMMs).
+ *   Parameters by their key in the detector's state_dict: "img_backbone.conv1.weight", "img_backbone.layer1.0.bn1.
+ *   running_mean", "img_neck.lateral_convs.0.conv.bias", ... (HOST fp32; `num_batches_tracked` is not a parameter).
+ *   forward: img dev f32 [num_images, 3, H, W] (mean/std-normalised, padded) -> out_l dev f32 [num_images, 256, h_l, w_l]
+ *   (any out may be NULL), the layout `extract_img_feat` hands to the head after its view(B, N, C, h, w). */
+typedef struct occb200_backbone occb200_backbone;
+occb200_backbone* occb200_backbone_create(int num_images, int img_h, int img_w, int precision, int use_tensor_cores);
+void occb200_backbone_destroy(occb200_backbone* e);
+int occb200_backbone_load_param(occb200_backbone* e, const char* key, const float* data, int64_t numel);
+int occb200_backbone_finalize(occb200_backbone* e);
+int occb200_backbone_level_shape(const occb200_backbone* e, int level, int* h, int* w);
+int occb200_backbone_forward(occb200_backbone* e, const float* img, float* out0, float* out1, float* out2, float* out3,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

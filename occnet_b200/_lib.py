@@ -46,6 +46,12 @@ SIGNATURES = {
     'occb200_linear_f32': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'occb200_layernorm_f32': (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     'occb200_gemm_bf16_tc': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    'occb200_backbone_create': (_vp, [_i, _i, _i, _i, _i]),
+    'occb200_backbone_destroy': (None, [_vp]),
+    'occb200_backbone_load_param': (_i, [_vp, ctypes.c_char_p, _vp, ctypes.c_int64]),
+    'occb200_backbone_finalize': (_i, [_vp]),
+    'occb200_backbone_level_shape': (_i, [_vp, _i, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
+    'occb200_backbone_forward': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

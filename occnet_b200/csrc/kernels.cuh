@@ -29,6 +29,17 @@ int launch_sca_fused(const T* value, const void* qproj, bool qproj_is_half, cons
                      T* out, uint8_t* hits, cudaStream_t stream);
 int launch_project_pillars(const ScaParams& sp, float* ref_cam, uint8_t* mask, cudaStream_t stream);
 
+// ---- backbone_kernels.cu (image backbone + neck, channels-last; first version, see the file header)
+template <typename T> int launch_nchw_to_nhwc_small(const float* src, T* dst, int N, int C, int H, int W, cudaStream_t stream);
+template <typename T>
+int launch_im2col_nhwc(const T* in, T* out, int N, int H, int W, int C, int KH, int KW, int stride, int pad, int Ho, int Wo,
+                       int Kpad, cudaStream_t stream);
+template <typename T> int launch_maxpool3x3s2_nhwc(const T* in, T* out, int N, int H, int W, int C, int Ho, int Wo, cudaStream_t stream);
+template <typename T> int launch_add_relu(const T* a, const T* b, T* out, int64_t n, cudaStream_t stream);
+template <typename T>
+int launch_upsample_add_nhwc(T* fine, const T* coarse, int N, int Hf, int Wf, int Hc, int Wc, int C, cudaStream_t stream);
+template <typename T> int launch_nhwc_to_nchw_f32(const T* src, float* dst, int N, int HW, int C, cudaStream_t stream);
+
 // ---- elementwise.cu
 // feats level l: [num_cams, C, h, w] f32 (NCHW) -> tokens [num_cams, Nv, C] T, + cams_embeds + level_embeds
 // (all levels in one launch; level_embeds [num_levels, C])

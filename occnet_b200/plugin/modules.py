@@ -22,7 +22,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..engine import OccEngine
-from ..mmcv_shim import (ATTENTION, DETECTORS, HEADS, TRANSFORMER, TRANSFORMER_LAYER, TRANSFORMER_LAYER_SEQUENCE,
+from ..mmcv_shim import (ATTENTION, BACKBONES, DETECTORS, HEADS, NECKS, TRANSFORMER, TRANSFORMER_LAYER, TRANSFORMER_LAYER_SEQUENCE,
                          BaseModule, ConfigDict, ConvModule, ModuleList, TransformerLayerSequence, build_attention,
                          build_feedforward_network, build_head, build_loss, build_norm_layer,
                          build_positional_encoding, build_transformer, build_transformer_layer_sequence,
@@ -494,29 +494,117 @@ class BEVFormerOccHead(BaseModule):
         return preds_dicts['occ'].argmax(-1), preds_dicts['flow']             # argmax(softmax(x)) == argmax(x)
 
 
+class _Bottleneck(nn.Module):
+    """Parameter container of one ResNet bottleneck (names = mmdet / torchvision: conv1..3, bn1..3, downsample.{0,1})."""
+
+    def __init__(self, inplanes, planes, stride, downsample):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False); self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False); self.bn2 = nn.BatchNorm2d(planes)   # style 'pytorch'
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False); self.bn3 = nn.BatchNorm2d(planes * 4)
+        if downsample:
+            self.downsample = nn.Sequential(nn.Conv2d(inplanes, planes * 4, 1, stride, bias=False), nn.BatchNorm2d(planes * 4))
+
+
+@BACKBONES.register_module()
+class ResNet(BaseModule):
+    """mmdet `ResNet` as the shipped config uses it (bevformer_base_occ.py:48-58): depth 50, out_indices (1,2,3), style
+    'pytorch', norm_eval.  A PARAMETER CONTAINER with the reference's `state_dict` keys (= torchvision's resnet50, which
+    `pretrained='torchvision://resnet50'` loads unchanged); the arithmetic is `occnet_b200.backbone.BackboneEngine`."""
+
+    def __init__(self, depth=50, num_stages=4, out_indices=(1, 2, 3), frozen_stages=-1, norm_cfg=None, norm_eval=True,
+                 style='pytorch', with_cp=False, pretrained=None, init_cfg=None, **kwargs):
+        super().__init__()
+        if depth != 50 or num_stages != 4 or style != 'pytorch' or tuple(out_indices) != (1, 2, 3):
+            raise NotImplementedError('libocc_b200 backbone: ResNet-50, 4 stages, style pytorch, out_indices (1,2,3) only')
+        self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        inplanes = 64
+        for s, (nblk, planes) in enumerate(zip((3, 4, 6, 3), (64, 128, 256, 512))):
+            blocks = [_Bottleneck(inplanes if i == 0 else planes * 4, planes, 2 if (i == 0 and s > 0) else 1, i == 0)
+                      for i in range(nblk)]
+            setattr(self, f'layer{s + 1}', nn.Sequential(*blocks))
+            inplanes = planes * 4
+
+    def forward(self, x):
+        raise RuntimeError('ResNet here is a parameter container; run BEVFormerOcc.extract_feat (BackboneEngine)')
+
+
+@NECKS.register_module()
+class FPN(BaseModule):
+    """mmdet `FPN` as configured in bevformer_base_occ.py:59-66 (start_level 0, add_extra_convs 'on_output', num_outs 4):
+    parameter container with the reference keys lateral_convs.{i}.conv.*, fpn_convs.{i}.conv.*."""
+
+    def __init__(self, in_channels=(512, 1024, 2048), out_channels=256, num_outs=4, start_level=0, end_level=-1,
+                 add_extra_convs='on_output', relu_before_extra_convs=True, no_norm_on_lateral=False, conv_cfg=None,
+                 norm_cfg=None, act_cfg=None, upsample_cfg=None, init_cfg=None, **kwargs):
+        super().__init__()
+        if (list(in_channels) != [512, 1024, 2048] or num_outs != 4 or start_level != 0 or add_extra_convs != 'on_output'
+                or norm_cfg is not None or act_cfg is not None or out_channels != 256):
+            raise NotImplementedError('libocc_b200 neck: the shipped FPN configuration only')
+
+        def cm(ci, co, k, stride=1):
+            m = nn.Module()
+            m.conv = nn.Conv2d(ci, co, k, stride, k // 2)
+            return m
+        self.lateral_convs = nn.ModuleList([cm(c, out_channels, 1) for c in in_channels])
+        self.fpn_convs = nn.ModuleList([cm(out_channels, out_channels, 3) for _ in in_channels] + [cm(out_channels, out_channels, 3, 2)])
+
+    def forward(self, feats):
+        raise RuntimeError('FPN here is a parameter container; run BEVFormerOcc.extract_feat (BackboneEngine)')
+
+
 @DETECTORS.register_module()
 class BEVFormerOcc(BaseModule):
-    """reference: detectors/bevformer_occ.py:20-270 (inference shell).  The image backbone / neck are third-party
-    mmdet modules outside the hot path: pass FPN features as `img_feats`, or plug a callable
-    `feature_extractor(img) -> list of (B, N, C, h, w)`."""
+    """reference: detectors/bevformer_occ.py:20-270 (inference shell).  `img_backbone` / `img_neck` are built as
+    parameter containers (so reference checkpoints load with their own keys).  Features come from, in this order:
+    `img_feats=` handed to forward / simple_test; a `feature_extractor(img)` callable; or -- opt-in, FIRST VERSION not
+    yet validated on a GPU -- `native_backbone=True`: `occnet_b200.backbone.BackboneEngine`."""
 
     def __init__(self, pts_bbox_head=None, img_backbone=None, img_neck=None, use_grid_mask=False, video_test_mode=False,
-                 train_cfg=None, test_cfg=None, pretrained=None, feature_extractor=None, **kwargs):
+                 train_cfg=None, test_cfg=None, pretrained=None, feature_extractor=None, native_backbone=False,
+                 backbone_precision='bf16', **kwargs):
         super().__init__()
         if pts_bbox_head is not None:
             pts_bbox_head = dict(pts_bbox_head)
             pts_bbox_head.pop('train_cfg', None); pts_bbox_head.pop('test_cfg', None)
         self.pts_bbox_head = build_head(pts_bbox_head)
         self.img_backbone_cfg, self.img_neck_cfg = img_backbone, img_neck
+        if img_backbone is not None and img_backbone.get('type') == 'ResNet':
+            self.img_backbone = BACKBONES.build(dict(img_backbone))
+        if img_neck is not None and img_neck.get('type') == 'FPN':
+            self.img_neck = NECKS.build(dict(img_neck))
         self.feature_extractor = feature_extractor
+        self.native_backbone, self.backbone_precision = native_backbone, backbone_precision
+        self._backbone_engine, self._backbone_key = None, None
         self.video_test_mode = video_test_mode
         self.prev_frame_info = {'prev_bev': None, 'scene_token': None, 'prev_pos': 0, 'prev_angle': 0}
 
+    def extract_img_feat(self, img, img_metas=None, len_queue=None):
+        """reference :66-99 (eval: GridMask is the identity).  img (B, N, 3, H, W) -> list of (B, N, 256, h_l, w_l)."""
+        from ..backbone import BackboneEngine
+        if img.dim() == 4:
+            img = img.unsqueeze(0)
+        B, N = img.shape[:2]
+        x = img.reshape(B * N, *img.shape[2:])
+        key = (str(x.device), tuple(x.shape), self.backbone_precision,
+               tuple(p._version for p in self.img_backbone.parameters()), tuple(p._version for p in self.img_neck.parameters()))
+        if self._backbone_engine is None or key != self._backbone_key:
+            sd = {k: v for k, v in self.state_dict().items() if k.startswith(('img_backbone.', 'img_neck.'))}
+            self._backbone_engine = BackboneEngine(sd, B * N, x.shape[-2:], precision=self.backbone_precision, device=str(x.device))
+            self._backbone_key = key
+        feats = self._backbone_engine.forward(x)
+        if len_queue is not None:
+            return [f.view(B // len_queue, len_queue, N, *f.shape[1:]) for f in feats]
+        return [f.view(B, N, *f.shape[1:]) for f in feats]
+
     def extract_feat(self, img, img_metas=None, len_queue=None):
-        if self.feature_extractor is None:
-            raise RuntimeError('BEVFormerOcc: no image backbone in libocc_b200 (mmdet ResNet/FPN are out of scope); '
-                               'pass img_feats=... or set feature_extractor')
-        return self.feature_extractor(img)
+        if self.feature_extractor is not None:
+            return self.feature_extractor(img)
+        if self.native_backbone and hasattr(self, 'img_backbone') and hasattr(self, 'img_neck'):
+            return self.extract_img_feat(img, img_metas, len_queue=len_queue)
+        raise RuntimeError('BEVFormerOcc: pass img_feats=..., set feature_extractor, or opt in to the (not yet GPU-validated) '
+                           'native ResNet-50 + FPN with native_backbone=True')
 
     def obtain_history_bev(self, feats_queue, img_metas_list):
         """reference: detectors/bevformer_occ.py:159-178 -- run the encoder over the history frames (oldest first), each

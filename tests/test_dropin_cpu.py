@@ -69,6 +69,31 @@ def test_shipped_config_loads_and_builds_unchanged():
         head([torch.zeros(1, 6, 256, h, w) for h, w in fixtures.CFG_FULL['level_shapes']], fixtures.make_img_metas(fixtures.CFG_FULL))
 
 
+@pytest.mark.skipif(not os.path.exists(REF_CFG), reason='reference tree not present (GPU box)')
+def test_backbone_neck_containers_have_reference_keys():
+    """img_backbone / img_neck of the shipped config build as parameter containers whose keys are the reference's
+    (mmdet ResNet == torchvision resnet50 minus fc; mmdet FPN lateral_convs / fpn_convs) and accept the oracle's
+    parameter dict unchanged."""
+    import projects.mmdet3d_plugin  # noqa: F401
+    from torchvision.models import resnet50
+    from oracle import backbone as OB
+    det = build_detector(Config.fromfile(REF_CFG).model)
+    sd = det.state_dict()
+    bk = {k[len('img_backbone.'):] for k in sd if k.startswith('img_backbone.')}
+    assert bk == {k for k in resnet50(weights=None).state_dict() if not k.startswith('fc.')}
+    nk = sorted(k for k in sd if k.startswith('img_neck.'))
+    assert nk == sorted(f'img_neck.{grp}.{i}.conv.{t}' for grp, n in (('lateral_convs', 3), ('fpn_convs', 4))
+                        for i in range(n) for t in ('weight', 'bias'))
+    p = OB.init_params(seed=5)
+    missing = det.load_state_dict(p, strict=False)
+    assert not missing.unexpected_keys
+    assert all(k.startswith('pts_bbox_head.') or k.endswith('num_batches_tracked') for k in missing.missing_keys)
+    with pytest.raises(RuntimeError):                                                       # containers only: no torch fallback
+        det.img_backbone(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(RuntimeError):
+        det.extract_feat(torch.zeros(1, 6, 3, 64, 64))
+
+
 def test_contiguous_shard_rule():
     from occnet_b200.dist import contiguous_shard
     assert contiguous_shard(10, 0, 2) == [0, 1, 2, 3, 4] and contiguous_shard(10, 1, 2) == [5, 6, 7, 8, 9]

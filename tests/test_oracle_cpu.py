@@ -243,3 +243,81 @@ def test_backbone_extract_img_feat_shapes():
         shapes.append((-(-h // s), -(-w // s)))
     shapes.append((-(-shapes[-1][0] // 2), -(-shapes[-1][1] // 2)))
     assert shapes == [tuple(s) for s in fixtures.CFG_FULL['level_shapes']]
+
+
+def test_backbone_engine_schedule_emulated_on_cpu():
+    """The backbone engine (csrc/backbone.cu) could not be run on a GPU in round 1.  This test re-states its SCHEDULE in
+    numpy -- NHWC activations, BN folded into tap-major weights [co][(ky*KW+kx)*Cin + c] zero-padded to 64, explicit
+    im2col with the same index arithmetic, GEMM, add+ReLU, nearest-by-size top-down add, extra stride-2 level on the last
+    output -- and checks it against the oracle, so that layout / ordering mistakes cannot hide behind CUDA syntax."""
+    from oracle import backbone as OB
+    p = {k: v.numpy() for k, v in OB.init_params(seed=7).items()}
+    pt = {k: torch.from_numpy(v) for k, v in p.items()}
+
+    def fold(conv, bn, k, conv_bias=False):
+        w = p[conv + '.weight']; co, ci = w.shape[:2]
+        scale, shift = np.ones(co, np.float32), np.zeros(co, np.float32)
+        if bn:
+            scale = p[bn + '.weight'] / np.sqrt(p[bn + '.running_var'] + np.float32(1e-5))
+            shift = p[bn + '.bias'] - p[bn + '.running_mean'] * scale
+        if conv_bias:
+            shift = shift + p[conv + '.bias'] * scale
+        kpad = (k * k * ci + 63) // 64 * 64
+        W = np.zeros((co, kpad), np.float32)
+        W[:, :k * k * ci] = (w.transpose(0, 2, 3, 1) * scale[:, None, None, None]).reshape(co, -1)   # (ky, kx, ci) order
+        return W, shift.astype(np.float32), kpad
+
+    def im2col(x, k, stride, pad, kpad):                       # x [N,H,W,C] -> [N*Ho*Wo, kpad]
+        N, H, W, C = x.shape
+        Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        out = np.zeros((N, Ho, Wo, kpad), np.float32)
+        for kk in range(kpad):
+            tap, c = divmod(kk, C)
+            if tap >= k * k:
+                continue
+            ky, kx = divmod(tap, k)
+            ys, xs = np.arange(Ho) * stride + ky - pad, np.arange(Wo) * stride + kx - pad
+            vy, vx = (ys >= 0) & (ys < H), (xs >= 0) & (xs < W)
+            out[:, vy[:, None] & vx[None, :], kk] = x[:, ys[vy]][:, :, xs[vx]][..., c].reshape(N, -1)
+        return out.reshape(-1, kpad), Ho, Wo
+
+    def conv(x, conv_key, bn_key, k, stride, pad, relu, conv_bias=False):
+        W, b, kpad = fold(conv_key, bn_key, k, conv_bias)
+        N, H, Wd, C = x.shape
+        if k == 1 and stride == 1 and kpad == C:
+            A, Ho, Wo = x.reshape(-1, C), H, Wd
+        else:
+            A, Ho, Wo = im2col(x, k, stride, pad, kpad)
+        y = A @ W.T + b
+        return (np.maximum(y, 0) if relu else y).reshape(N, Ho, Wo, -1)
+
+    img = torch.randn(1, 3, 72, 104, generator=torch.Generator().manual_seed(4))
+    x = img.numpy().transpose(0, 2, 3, 1)                                            # nchw_to_nhwc_small
+    x = conv(x, 'img_backbone.conv1', 'img_backbone.bn1', 7, 2, 3, True)
+    x = torch.nn.functional.max_pool2d(torch.from_numpy(x).permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).numpy()
+    stage_out = []
+    for s, nblk in enumerate((3, 4, 6, 3)):
+        for i in range(nblk):
+            pre = f'img_backbone.layer{s + 1}.{i}.'
+            stride = 2 if (i == 0 and s > 0) else 1
+            t = conv(x, pre + 'conv1', pre + 'bn1', 1, 1, 0, True)
+            t = conv(t, pre + 'conv2', pre + 'bn2', 3, stride, 1, True)
+            t = conv(t, pre + 'conv3', pre + 'bn3', 1, 1, 0, False)
+            idn = conv(x, pre + 'downsample.0', pre + 'downsample.1', 1, stride, 0, False) if i == 0 else x
+            x = np.maximum(t + idn, 0)
+        if s >= 1:
+            stage_out.append(x)
+    lat = [conv(c, f'img_neck.lateral_convs.{i}.conv', None, 1, 1, 0, False, True) for i, c in enumerate(stage_out)]
+    for i in (2, 1):
+        Hf, Wf, Hc, Wc = lat[i - 1].shape[1], lat[i - 1].shape[2], lat[i].shape[1], lat[i].shape[2]
+        sy = np.minimum(np.floor(np.arange(Hf, dtype=np.float32) * (np.float32(Hc) / np.float32(Hf))).astype(int), Hc - 1)
+        sx = np.minimum(np.floor(np.arange(Wf, dtype=np.float32) * (np.float32(Wc) / np.float32(Wf))).astype(int), Wc - 1)
+        lat[i - 1] = lat[i - 1] + lat[i][:, sy][:, :, sx]
+    outs = [conv(l, f'img_neck.fpn_convs.{i}.conv', None, 3, 1, 1, False, True) for i, l in enumerate(lat)]
+    outs.append(conv(outs[2], 'img_neck.fpn_convs.3.conv', None, 3, 2, 1, False, True))
+    with torch.no_grad():
+        want = OB.fpn(pt, OB.resnet50(pt, img))
+    for o, w in zip(outs, want):
+        got = torch.from_numpy(o).permute(0, 3, 1, 2)                                # nhwc_to_nchw_f32
+        assert got.shape == w.shape
+        assert (got - w).abs().max().item() < 2e-3 * max(1.0, w.abs().max().item()), (got - w).abs().max()
