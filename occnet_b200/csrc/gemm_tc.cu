@@ -3,13 +3,20 @@
 // Every nn.Linear on the path has this shape (reference: temporal_self_attention.py:99-104,
 // spatial_cross_attention.py:67,245-249, mmcv FFN) with K in {256,512}, N in {192,256,512,768}.
 //
-// Persistent, warp-specialised kernel, one CTA per SM:
-//   warp 0   TMA producer : A tile 128x64 + W tile BNx64 (bf16, 128B swizzle) per k-block, 4-stage mbarrier ring
+// Persistent, warp-specialised kernel, one CTA per SM; every CTA owns one n-block and a contiguous range of rows
+// (dealt in 32-row blocks so that all CTAs move the same number of bytes):
+//   warp 0   TMA producer : the CTA's weight block once (resident, <= 128 KB, one mbarrier per 32 KB k-slice) or a W
+//                           k-block per stage; A tiles 128x64 (bf16, 128B swizzle) through a 3-6 stage mbarrier ring
 //   warp 1   MMA issuer   : tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16 x4 per stage;
 //                           accumulators double-buffered in TMEM (2 x 256 columns)
-//   warps 2-9 epilogue    : tcgen05.ld 32x32b -> bias / ReLU / residual -> global store (fp32 or bf16), or the fused
-//                           LayerNorm (x written back to TMEM with tcgen05.st, row statistics, second pass);
-//                           overlaps the next tile's main loop.  Weights stay resident in shared memory when they fit.
+//   warps 2-9 epilogue    : tcgen05.ld 32x32b, overlapping the next tile's main loop.  Per-column constants (bias,
+//                           gamma, beta) are staged in shared memory once per CTA.  Three variants:
+//                           (a) 16-bit output: bias / ReLU -> bf16 or fp16 -> swizzled 2 KB staging -> TMA store;
+//                           (b) fused LayerNorm: x = acc + bias + residual written back to TMEM (tcgen05.st), row
+//                               statistics exchanged between the two column-half warps, second pass normalises;
+//                               fp32 residual stream in the T32 block layout, bf16 operand copy via staging;
+//                           (c) fp32 output (+ residual) via swizzled staging, 4 rows x 128 B per store instruction.
+// Programmatic dependent launch: the prologue (barriers, TMEM, weights, constants) does not wait for the previous grid.
 // The A operand may be the concatenation of two matrices along K (TSA's cat([value, query+pos]),
 // temporal_self_attention.py:197) -- two tensor maps, no materialised concat.
 #include <cstdlib>

@@ -321,3 +321,54 @@ def test_backbone_engine_schedule_emulated_on_cpu():
         got = torch.from_numpy(o).permute(0, 3, 1, 2)                                # nhwc_to_nchw_f32
         assert got.shape == w.shape
         assert (got - w).abs().max().item() < 2e-3 * max(1.0, w.abs().max().item()), (got - w).abs().max()
+
+
+@pytest.mark.parametrize('X,Y,grid', [(200, 200, 148), (50, 50, 148), (40, 40, 148), (7, 9, 3), (5, 8, 1), (33, 17, 20)])
+def test_conv3d_plane_major_schedule_covers_every_tap_once(X, Y, grid):
+    """Python mirror of the MMA-issue loop of csrc/conv3d_tc.cu (plane-major, N = 96 windows over a ring of 8 TMEM
+    slots): every output tile must receive each of its 27 taps exactly once, with the weight sub-tile of that tap, in a
+    slot that is not reused before the tile completed, for any volume size and grid."""
+    SLOTS, TILE_Y = 8, 8
+    y_tiles = (Y + TILE_Y - 1) // TILE_Y
+    total = X * y_tiles
+    grid = min(grid, total)
+    for cta in range(grid):
+        t_begin, t_end = total * cta // grid, total * (cta + 1) // grid
+        acc = {}                                                # output n -> list of (plane, t9, resident weight tile)
+        live_slot = {}                                          # slot -> output n currently accumulating there
+        done = set()
+        n_base, t = 0, t_begin
+        while t < t_end:
+            xa = t % X
+            xb = min(X, xa + (t_end - t))
+            p_lo, p_hi = max(xa - 1, 0), min(xb, X - 1)
+            for p in range(p_lo, p_hi + 1):
+                x_lo, x_hi = max(p - 1, xa), min(p + 1, xb - 1)
+                cnt, off = x_hi - x_lo + 1, x_lo - (p - 1)
+                assert 1 <= cnt <= 3 and 0 <= off and off + cnt <= 3
+                n_lo = n_base + (x_lo - xa)
+                slot_lo = n_lo & (SLOTS - 1)
+                first = min(cnt, SLOTS - slot_lo)
+                for x in range(x_lo, x_hi + 1):                 # outputs opening on this plane claim their slot
+                    if max(x - 1, 0) == p:
+                        n = n_base + (x - xa)
+                        s = n & (SLOTS - 1)
+                        assert s not in live_slot or live_slot[s] in done, 'slot reused before its tile completed'
+                        live_slot[s] = n
+                        acc[n] = []
+                for t9 in range(9):
+                    for j in range(cnt):                        # window position j -> slot, weight sub-tile off + j
+                        slot = (slot_lo + j) if j < first else (j - first)
+                        n = n_lo + j
+                        assert slot == n & (SLOTS - 1) and live_slot[slot] == n
+                        acc[n].append((p, t9, t9 * 3 + off + j))
+                for x in range(x_lo, x_hi + 1):
+                    if min(x + 1, X - 1) == p:
+                        done.add(n_base + (x - xa))
+            n_base += xb - xa
+            t += xb - xa
+        assert len(acc) == t_end - t_begin and done == set(acc)
+        for i, tt in enumerate(range(t_begin, t_end)):          # epilogue order: n-th tile of the CTA = tile t_begin + n
+            x = tt % X
+            want = sorted((x + dx - 1, t9, t9 * 3 + (2 - dx)) for dx in range(3) for t9 in range(9) if 0 <= x + dx - 1 < X)
+            assert sorted(acc[i]) == want, (cta, tt)
