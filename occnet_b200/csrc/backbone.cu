@@ -11,12 +11,14 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
 
 #include "../../include/occ_b200.h"
 #include "common.cuh"
+#include "conv2d_tc.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 
@@ -141,14 +143,32 @@ int conv_gemm(occb200_backbone* e, const T* A, int64_t M, const ConvW& c, T* out
                            c.cout, c.kpad, act, st);
 }
 
-// one convolution on NHWC input [N, H, W, cin] -> out [N, Ho, Wo, cout]
+// OCC_BACKBONE_IMPLICIT=1: stride-1 3x3 convolutions (and 1x1 + residual) go through the TMA-im2col kernel conv2d_tc.cu
+bool implicit_enabled()
+{
+    static const bool on = getenv("OCC_BACKBONE_IMPLICIT") != nullptr && atoi(getenv("OCC_BACKBONE_IMPLICIT")) != 0;
+    return on;
+}
+
+// one convolution on NHWC input [N, H, W, cin] -> out [N, Ho, Wo, cout].  `residual` (same shape as out) is only
+// accepted on the implicit-GEMM path, where the add (+ ReLU) is fused into the epilogue; fused_residual reports it.
 template <typename T>
 int conv(occb200_backbone* e, const T* in, int N, int H, int W, const ConvW& c, T* out, int act, int& Ho, int& Wo,
-         cudaStream_t st)
+         cudaStream_t st, const T* residual = nullptr, bool* fused_residual = nullptr)
 {
     Ho = out_size(H, c.kh, c.stride, c.pad);
     Wo = out_size(W, c.kw, c.stride, c.pad);
     const int64_t M = (int64_t)N * Ho * Wo;
+    if (fused_residual) *fused_residual = false;
+    if constexpr (sizeof(T) == 2) {
+        if (e->use_tc && implicit_enabled() && c.wh.p && c.stride == 1 && c.kpad == c.kh * c.kw * c.cin &&
+            conv2d_tc_supported(c.cin, c.cout, c.kh, c.kw) && (c.kh == 3 || residual != nullptr)) {
+            if (fused_residual) *fused_residual = residual != nullptr;
+            return conv2d_tc(reinterpret_cast<const bf16*>(in), c.wh.as<bf16>(), c.b.as<float>(),
+                             reinterpret_cast<const bf16*>(residual), reinterpret_cast<bf16*>(out), N, H, W, c.cin, c.cout,
+                             c.kh, c.kw, c.pad, residual ? ACT_RELU : act, st);
+        }
+    }
     const T* A = in;
     if (!(c.kh == 1 && c.kw == 1 && c.stride == 1 && c.kpad == c.cin)) {
         OCC_CHECK((size_t)M * c.kpad * sizeof(T) <= e->col.bytes, "backbone: im2col workspace too small");
@@ -178,18 +198,24 @@ int forward_impl(occb200_backbone* e, const float* img, float* const* outs, cuda
             int h1, w1, h2, w2, h3, w3;
             if (conv<T>(e, cur, N, H, W, blk.c1, e->t1.as<T>(), ACT_RELU, h1, w1, st)) return 2;
             if (conv<T>(e, e->t1.as<T>(), N, h1, w1, blk.c2, e->t2.as<T>(), ACT_RELU, h2, w2, st)) return 2;
-            if (conv<T>(e, e->t2.as<T>(), N, h2, w2, blk.c3, e->t3.as<T>(), ACT_NONE, h3, w3, st)) return 2;
             const T* identity = cur;
             if (blk.has_down) {
                 int hd, wd;
                 if (conv<T>(e, cur, N, H, W, blk.down, e->idn.as<T>(), ACT_NONE, hd, wd, st)) return 2;
-                OCC_CHECK(hd == h3 && wd == w3, "backbone: downsample / main path shape mismatch");
                 identity = e->idn.as<T>();
             }
             const bool last = b + 1 == e->blocks[s].size();
             T* dst = (cur == e->ping[0].as<T>()) ? e->ping[1].as<T>() : e->ping[0].as<T>();
             if (last && s >= 1) dst = e->stage_out[s - 1].as<T>();           // C3 / C4 / C5 stay alive for the neck
-            if (launch_add_relu<T>(e->t3.as<T>(), identity, dst, (int64_t)N * h3 * w3 * blk.c3.cout, st)) return 2;
+            // conv3 (1x1): on the implicit-GEMM path the residual add + ReLU ride its epilogue and it writes `dst` directly
+            bool fused = false;
+            if (implicit_enabled()) {
+                if (conv<T>(e, e->t2.as<T>(), N, h2, w2, blk.c3, dst, ACT_NONE, h3, w3, st, identity, &fused)) return 2;
+            }
+            if (!fused) {
+                if (conv<T>(e, e->t2.as<T>(), N, h2, w2, blk.c3, e->t3.as<T>(), ACT_NONE, h3, w3, st)) return 2;
+                if (launch_add_relu<T>(e->t3.as<T>(), identity, dst, (int64_t)N * h3 * w3 * blk.c3.cout, st)) return 2;
+            }
             cur = dst; H = h3; W = w3;
         }
         if (s >= 1) { sh[s - 1] = H; sw[s - 1] = W; }

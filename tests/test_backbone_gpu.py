@@ -1,7 +1,11 @@
 """Parity of the FIRST-VERSION image backbone + neck (ResNet-50 + FPN) against its oracle.
 
 OPT-IN: these tests run only with OCC_EXPERIMENTAL=1.  The kernels were written after the round-1 GPU budget was spent
-and have not been run on a GPU yet; they must not gate the validated hot path's `pytest -m gpu` tier until they have."""
+and have not been run on a GPU yet; they must not gate the validated hot path's `pytest -m gpu` tier until they have.
+
+    OCC_EXPERIMENTAL=1 python -m pytest tests/test_backbone_gpu.py -q                              # im2col + gemm_tc
+    OCC_EXPERIMENTAL=1 OCC_BACKBONE_IMPLICIT=1 python -m pytest tests/test_backbone_gpu.py -q -k tcgen05   # + conv2d_tc.cu
+"""
 import os
 
 import pytest
