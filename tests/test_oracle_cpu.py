@@ -372,3 +372,64 @@ def test_conv3d_plane_major_schedule_covers_every_tap_once(X, Y, grid):
             x = tt % X
             want = sorted((x + dx - 1, t9, t9 * 3 + (2 - dx)) for dx in range(3) for t9 in range(9) if 0 <= x + dx - 1 < X)
             assert sorted(acc[i]) == want, (cta, tt)
+
+
+@pytest.mark.parametrize('M,n_tiles,sms', [(40000, 1, 148), (40000, 3, 148), (184950, 6, 148), (130, 1, 148), (31, 1, 148),
+                                           (2227200, 8, 148), (4097, 2, 7)])
+def test_gemm_row_ranges_cover_every_row_once(M, n_tiles, sms):
+    """Python mirror of gemm_tc.cu's CTA -> (n block, row range) mapping: ranges are dealt in 32-row blocks, every row of
+    every n-block is owned by exactly one CTA, every CTA owns at least one block, and the spread is at most one block."""
+    m_tiles = (M + 127) // 128
+    per_n = max(1, min(sms // n_tiles, m_tiles))
+    grid = per_n * n_tiles
+    nb32 = (M + 31) >> 5
+    owned = {n: [] for n in range(n_tiles)}
+    for cta in range(grid):
+        n_blk, grp, ngrp = cta % n_tiles, cta // n_tiles, grid // n_tiles
+        row_begin = ((nb32 * grp) // ngrp) << 5
+        row_end = min(M, ((nb32 * (grp + 1)) // ngrp) << 5)
+        assert row_begin < row_end and row_begin % 32 == 0
+        owned[n_blk].append((row_begin, row_end))
+    for n, rs in owned.items():
+        rs.sort()
+        assert rs[0][0] == 0 and rs[-1][1] == M
+        assert all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+        blocks = [(e - b + 31) // 32 for b, e in rs]
+        assert max(blocks) - min(blocks) <= 1
+
+
+def test_clamped_2x2_fetch_block_equals_zero_padded_bilinear():
+    """Python mirror of msda.cu `prep_sample`: the gather kernels always fetch the 2x2 pixel block whose top-left corner is
+    clamped to [0,H-2]x[0,W-2] and re-assign the bilinear corner weights to the positions of that block that coincide with
+    in-bounds true corners.  Must equal zero-padded bilinear sampling (mmcv ms_deform_attn_im2col_bilinear) everywhere,
+    including the one-pixel border band and fully outside positions."""
+    rng = np.random.default_rng(0)
+    for H, W in ((2, 2), (3, 5), (15, 25), (116, 200)):
+        img = rng.standard_normal((H, W)).astype(np.float64)
+        pts = np.concatenate([rng.uniform(-2.5, max(H, W) + 1.5, size=(4000, 2)),
+                              np.array([[-1.0, -1.0], [-0.999, 0.3], [H - 1, W - 1], [H - 0.001, W - 0.001], [H, 0], [0, W],
+                                        [-0.5, -0.5], [H - 0.5, W - 0.5], [0.0, 0.0], [H - 1.0, 0.0]])])
+        for h_im, w_im in pts:
+            valid = h_im > -1 and w_im > -1 and h_im < H and w_im < W
+            # reference: zero padding outside, corners (h_lo, w_lo) .. (h_lo+1, w_lo+1)
+            want = 0.0
+            if valid:
+                h_lo, w_lo = int(np.floor(h_im)), int(np.floor(w_im))
+                lh, lw = h_im - h_lo, w_im - w_lo
+                for dy, dx, wt in ((0, 0, (1 - lh) * (1 - lw)), (0, 1, (1 - lh) * lw), (1, 0, lh * (1 - lw)), (1, 1, lh * lw)):
+                    y, x = h_lo + dy, w_lo + dx
+                    if 0 <= y < H and 0 <= x < W:
+                        want += wt * img[y, x]
+            # kernel: clamped block + re-assigned weights
+            hf, wf = (np.floor(h_im), np.floor(w_im)) if valid else (0.0, 0.0)
+            h_lo, w_lo = int(hf), int(wf)
+            lh, lw = h_im - hf, w_im - wf
+            hh, hw = 1 - lh, 1 - lw
+            hb, wb = min(max(h_lo, 0), H - 2), min(max(w_lo, 0), W - 2)
+            rw0 = hh if h_lo == hb else (lh if h_lo + 1 == hb else 0.0)
+            rw1 = hh if h_lo == hb + 1 else (lh if h_lo == hb else 0.0)
+            cw0 = hw if w_lo == wb else (lw if w_lo + 1 == wb else 0.0)
+            cw1 = hw if w_lo == wb + 1 else (lw if w_lo == wb else 0.0)
+            g = 1.0 if valid else 0.0
+            got = g * (rw0 * cw0 * img[hb, wb] + rw0 * cw1 * img[hb, wb + 1] + rw1 * cw0 * img[hb + 1, wb] + rw1 * cw1 * img[hb + 1, wb + 1])
+            assert abs(got - want) < 1e-12, (H, W, h_im, w_im, got, want)
