@@ -298,6 +298,7 @@ def run_ours(args):
                 tensor_tflops=round(work['gemm_flops'] / (rooflines['gemm']['ms_per_frame'] * 1e-3) / 1e12, 1)
                 if 'gemm' in rooflines else None)
     cpu = cpu_baseline(cfg, sample_layers=args.cpu_layers) if (world == 1 and not args.no_cpu) else None
+    backbone = run_backbone_leg(args, cfg, eng, dev, want) if (args.with_backbone and world == 1) else None
     line = {
         'metric': METRIC, 'value': round(world * args.steps / (ms_max * 1e-3), 2), 'unit': 'samples/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
@@ -321,10 +322,39 @@ def run_ours(args):
         'kernel_share': share,
         'kernel_ms_per_frame': {k: round(v[0] / args.steps, 4) for k, v in prof.items()},
         'cpu_baseline': cpu,
+        **({'backbone_experimental': backbone} if backbone is not None else {}),
         'ray_metric': {'miou': fin['miou'], 'mave': fin['mave'], 'score': fin['score'], 'frames': world,
                        'collective': 'all_reduce(sum) of 187 fp64 counters' if world > 1 else 'none (1 rank)'},
     }
     print(json.dumps(line))
+
+
+def run_backbone_leg(args, cfg, eng, dev, want):
+    """EXPERIMENTAL (--with-backbone): images -> ResNet-50 + FPN (occb200_backbone_*, first version) ->
+    the hot path.  Not part of the headline numbers; reported under its own key."""
+    from occnet_b200.backbone import BackboneEngine
+    H, W = cfg['img_shape'][:2]
+    nc = cfg['num_cams']
+    be = BackboneEngine(fixtures.init_backbone_params(seed=5), nc, (H, W), precision=args.precision,
+                        use_tensor_cores=bool(args.tc) and args.precision == 'bf16', device=str(dev))
+    imgs = [torch.randn(nc, 3, H, W, device=dev, generator=torch.Generator(device=dev).manual_seed(7 + i)) for i in range(2)]
+    assert be.level_shapes == [tuple(s) for s in cfg['level_shapes']], be.level_shapes
+    for i in range(3):
+        eng.forward(be.forward(imgs[i % 2]), want=want)
+    torch.cuda.synchronize()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    for i in range(args.steps):
+        feats = be.forward(imgs[i % 2])
+    e1.record()
+    for i in range(args.steps):
+        eng.forward(be.forward(imgs[i % 2]), want=want)
+    e2.record()
+    torch.cuda.synchronize()
+    bb_ms, chain_ms = e0.elapsed_time(e1) / args.steps, e1.elapsed_time(e2) / args.steps
+    return {'status': 'first version of the backbone, not at the parity bar yet', 'backbone_ms_per_frame': round(bb_ms, 4),
+            'images_to_voxels_ms_per_frame': round(chain_ms, 4), 'images_to_voxels_samples_per_s': round(1e3 / chain_ms, 2),
+            'backbone_gflop_per_frame': 1460.0, 'implicit_gemm': bool(os.environ.get('OCC_BACKBONE_IMPLICIT'))}
 
 
 def pick_cpu_threads():
@@ -438,6 +468,8 @@ def main():
     ap.add_argument('--tc', type=int, default=1, help='tcgen05 tensor-core kernels (bf16 only)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--cpu-layers', type=int, default=None, help='bound the cpu_baseline sample to this many layers')
+    ap.add_argument('--with-backbone', action='store_true',
+                    help='EXPERIMENTAL: also time images -> ResNet-50+FPN -> hot path (backbone not yet GPU-validated)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

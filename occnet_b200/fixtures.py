@@ -181,3 +181,49 @@ def init_params(cfg, seed=2, perturb=True, num_embed_levels=None):
         p[f'transformer.{name}.2.weight'] = xavier(out, od * 2)
         p[f'transformer.{name}.2.bias'] = torch.randn(out, generator=g) * 0.05
     return p
+
+
+# ---- image backbone + neck (ResNet-50 + FPN, reference config bevformer_base_occ.py:48-66): synthetic parameters
+_RESNET50_BLOCKS, _RESNET50_PLANES = (3, 4, 6, 3), (64, 128, 256, 512)
+
+
+def init_backbone_params(seed=5, out_channels=256, bn_stats=True):
+    """Random parameters with the reference's `state_dict` key names (img_backbone.* / img_neck.*): Kaiming-normal
+    convolutions (mmdet `ResNet.init_weights`), BatchNorm gamma=1 / beta=0 perturbed, running statistics perturbed so
+    that a BN-folding bug cannot hide; FPN convs Xavier-uniform with perturbed biases."""
+    g = torch.Generator().manual_seed(seed)
+    p = {}
+
+    def conv(name, co, ci, k):
+        fan_out = co * k * k
+        p[name + '.weight'] = torch.randn(co, ci, k, k, generator=g) * (2.0 / fan_out) ** 0.5
+
+    def bn(name, c):
+        p[name + '.weight'] = 1.0 + 0.1 * torch.randn(c, generator=g)
+        p[name + '.bias'] = 0.1 * torch.randn(c, generator=g)
+        p[name + '.running_mean'] = (0.1 * torch.randn(c, generator=g)) if bn_stats else torch.zeros(c)
+        p[name + '.running_var'] = (0.5 + torch.rand(c, generator=g)) if bn_stats else torch.ones(c)
+
+    b = 'img_backbone.'
+    conv(b + 'conv1', 64, 3, 7); bn(b + 'bn1', 64)
+    inplanes = 64
+    for s, (nblk, planes) in enumerate(zip(_RESNET50_BLOCKS, _RESNET50_PLANES)):
+        for i in range(nblk):
+            pre = f'{b}layer{s + 1}.{i}.'
+            conv(pre + 'conv1', planes, inplanes, 1); bn(pre + 'bn1', planes)
+            conv(pre + 'conv2', planes, planes, 3); bn(pre + 'bn2', planes)
+            conv(pre + 'conv3', planes * 4, planes, 1); bn(pre + 'bn3', planes * 4)
+            if i == 0:
+                conv(pre + 'downsample.0', planes * 4, inplanes, 1); bn(pre + 'downsample.1', planes * 4)
+            inplanes = planes * 4
+    nk = 'img_neck.'
+    for i, ci in enumerate((512, 1024, 2048)):
+        w = torch.empty(out_channels, ci, 1, 1)
+        bound = (6.0 / (ci + out_channels)) ** 0.5
+        p[f'{nk}lateral_convs.{i}.conv.weight'] = (torch.rand(w.shape, generator=g) * 2 - 1) * bound
+        p[f'{nk}lateral_convs.{i}.conv.bias'] = 0.05 * torch.randn(out_channels, generator=g)
+    for i in range(4):
+        bound = (6.0 / (out_channels * 9 * 2)) ** 0.5
+        p[f'{nk}fpn_convs.{i}.conv.weight'] = (torch.rand(out_channels, out_channels, 3, 3, generator=g) * 2 - 1) * bound
+        p[f'{nk}fpn_convs.{i}.conv.bias'] = 0.05 * torch.randn(out_channels, generator=g)
+    return p
