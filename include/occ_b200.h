@@ -73,7 +73,11 @@ typedef struct occb200_config {
     float pc_range[6];
     int precision;                 /* 0 = fp32 storage + fp32 CUDA-core GEMMs (parity config),
                                       1 = bf16 storage, fp32 accumulate (throughput config)                  */
-    int use_tensor_cores;          /* 1 = tcgen05 GEMM / conv kernels where available (precision 1 only)     */
+    int use_tensor_cores;          /* 1 = tcgen05 GEMM / conv kernels where available                       */
+    int use_cams_embeds;           /* TransformerOcc(use_cams_embeds=...), transformer_occ.py:214-215; 0 = the
+                                      camera embedding is NOT added to the packed features                    */
+    int rotate_center[2];          /* TransformerOcc(rotate_center=[100,100]), transformer_occ.py:200: centre
+                                      (x, y) of the prev_bev rotation done by occb200_engine_forward_prev      */
 } occb200_config;
 
 int occb200_engine_create(const occb200_config* cfg, occb200_engine** out);
@@ -120,7 +124,8 @@ int occb200_engine_wait_host(occb200_engine* e, int slot);
 
 /* Intermediate taps for parity tests (dev f32, valid after a forward; NULL if not produced):
  *   which: 0 = layer output [Nq,C] of layer `layer`; 1 = TSA output (pre-norm, with residual); 2 = SCA output
- *   (pre-norm, with residual); 3 = voxel features [X,Y,Z,out_dim] (converted to fp32 into `dst`). */
+ *   (pre-norm, with residual); 3 = voxel features [X,Y,Z,out_dim] (converted to fp32 into `dst`);
+ *   4 = packed camera tokens [num_cams, Nv, C] of the last frame (get_bev_features, transformer_occ.py:207-227). */
 int occb200_engine_enable_taps(occb200_engine* e, int enable);
 int occb200_engine_copy_tap(occb200_engine* e, int which, int layer, float* dst_dev, void* stream);
 

@@ -17,7 +17,8 @@ class OccConfig(ctypes.Structure):
                 ('num_cams', _i), ('num_levels', _i), ('level_h', _i * 4), ('level_w', _i * 4),
                 ('num_points_in_pillar', _i), ('sca_points', _i), ('tsa_points', _i), ('ffn_dim', _i),
                 ('pillar_h', _i), ('out_dim', _i), ('num_classes', _i), ('pc_range', ctypes.c_float * 6),
-                ('precision', _i), ('use_tensor_cores', _i)]
+                ('precision', _i), ('use_tensor_cores', _i), ('use_cams_embeds', _i),
+                ('rotate_center', _i * 2)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/occ_b200.h

@@ -255,17 +255,8 @@ int conv2d_tc(const bf16* in, const bf16* w_tap_major, const float* bias, const 
         tmRes = tmOut;
         if (residual && make_tensor_map_bf16(&tmRes, residual, 4, dims, strides, box, 64)) return 1;
     }
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        OCC_CUDA(cudaGetDevice(&dev));
-        OCC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    static bool attr_set = false;
-    if (!attr_set) {
-        OCC_CUDA(cudaFuncSetAttribute(conv2d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        attr_set = true;
-    }
+    const int num_sms = sm_count_current_device();
+    OCC_CUDA(cudaFuncSetAttribute(conv2d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));   // per device
     const int m_tiles = N * ((H + TILE_H - 1) / TILE_H) * ((W + TILE_W - 1) / TILE_W), n_tiles = Cout / BN;
     int per_n = num_sms / n_tiles;
     if (per_n < 1) per_n = 1;

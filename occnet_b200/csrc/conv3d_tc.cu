@@ -222,12 +222,7 @@ int launch_conv3d_tc(const bf16* in, const bf16* w_tap_major, const float* bias,
     }
     const int a_bytes = BLOCK_M * row_bytes, w_bytes = (TAPS * COUT * row_bytes + 1023) & ~1023;
     const int smem = 1024 + w_bytes + STAGES * a_bytes + BAR_BYTES;
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        OCC_CUDA(cudaGetDevice(&dev));
-        OCC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int num_sms = sm_count_current_device();
     const int tiles = X * ((Y + TILE_Y - 1) / TILE_Y);
     const int grid = tiles < num_sms ? tiles : num_sms;
     if (Cin == 16) {

@@ -560,7 +560,9 @@ int occb200_engine_finalize(occb200_engine* e)
         dre.release(); dce.release();
         GETP(le, "transformer.level_embeds", (size_t)c.num_levels * C);
         GETP(cm, "transformer.cams_embeds", (size_t)c.num_cams * C);
-        if (upload(e->level_embeds, le->data(), le->size()) || upload(e->cams_embeds, cm->data(), cm->size())) return 2;
+        std::vector<float> cams(*cm);
+        if (!c.use_cams_embeds) std::fill(cams.begin(), cams.end(), 0.f);    // transformer_occ.py:214-215: added only if set
+        if (upload(e->level_embeds, le->data(), le->size()) || upload(e->cams_embeds, cams.data(), cams.size())) return 2;
     }
     for (int l = 0; l < c.num_layers; ++l) {
         LayerW& w = e->layers[l];
@@ -858,6 +860,14 @@ int occb200_engine_copy_tap(occb200_engine* e, int which, int layer, float* dst,
             return 0;
         }
         return launch_bf16_to_f32(e->vox2.as<bf16>(), dst, (int64_t)nv, st);
+    }
+    if (which == 4) {                                            // packed camera tokens [num_cams, Nv, C] (row a9)
+        const size_t nt = (size_t)e->cfg.num_cams * e->Nv * 256;
+        if (e->cfg.precision == 0) {
+            OCC_CUDA(cudaMemcpyAsync(dst, e->tokens.p, nt * 4, cudaMemcpyDeviceToDevice, st));
+            return 0;
+        }
+        return launch_bf16_to_f32(e->tokens.as<bf16>(), dst, (int64_t)nt, st);
     }
     set_last_error("unknown tap");
     return 1;

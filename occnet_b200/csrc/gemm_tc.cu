@@ -587,17 +587,9 @@ int launch(const bf16* A, const bf16* A2, int K1, const bf16* W, const float* bi
             c_tma = 1;
         }
     }
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        OCC_CUDA(cudaGetDevice(&dev));
-        OCC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    static bool attr_set = false;
-    if (!attr_set) {
-        OCC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<TC, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        attr_set = true;
-    }
+    const int num_sms = sm_count_current_device();
+    // per-device attribute (cheap): a process-wide `static bool` would leave a second device without the opt-in
+    OCC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<TC, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = N / p.BN;
     int per_n = num_sms / n_tiles;
     if (per_n > m_tiles) per_n = m_tiles;                        // (row ranges are dealt in 32-row blocks: >= 1 per CTA)

@@ -251,12 +251,7 @@ int launch_occ_head_tc(const bf16* vox, const bf16* w1cat, const bf16* w2cat, co
     }
     const int smem = 1024 + W1_BYTES + 2 * W2_CHUNK_BYTES + A_STAGES * A_BYTES + 4 * H_CHUNK_BYTES +
                      4 * 32 * MAX_CLS * 4 + (HID + NOUT) * 4 + 64 + 256;
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        OCC_CUDA(cudaGetDevice(&dev));
-        OCC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int num_sms = sm_count_current_device();
     const int tiles = (int)((nvox + BLOCK_M - 1) / BLOCK_M);
     const int grid = tiles < num_sms ? tiles : num_sms;
     OCC_CUDA(cudaFuncSetAttribute(head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -171,6 +171,17 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N)
 
 }  // namespace tc
 
+// ---------------------------------------------------------------- host: per-device launch facts
+// (one process may drive engines on several devices: nothing here may be cached process-wide)
+inline int sm_count_current_device()
+{
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cache[dev] == 0) cudaDeviceGetAttribute(&cache[dev], cudaDevAttrMultiProcessorCount, dev);
+    return cache[dev] > 0 ? cache[dev] : 148;
+}
+
 // ---------------------------------------------------------------- host: tensor-map encoding without linking libcuda
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

@@ -20,6 +20,15 @@ def contiguous_shard(num_samples_total, rank, world_size):
     return indices[rank * per:(rank + 1) * per]
 
 
+def owned_unique(num_samples_total, rank, world_size):
+    """Positions (within `contiguous_shard(...)`) of the frames this rank must COUNT: the wrap-around padding
+    duplicates frames 0.. on the last rank(s); the reference drops them again after collection
+    (`apis/test.py:130`: results[:len(dataset)]), so a SUM all-reduce of per-rank counters must skip them."""
+    per = int(math.ceil(num_samples_total * 1.0 / world_size))
+    first = rank * per
+    return [i for i in range(per) if first + i < num_samples_total]
+
+
 def init_from_env(backend=None):
     """torchrun-style rendezvous (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*).  Returns (rank, local_rank, world)."""
     world = int(os.environ.get('WORLD_SIZE', '1'))

@@ -29,6 +29,9 @@ def _cfg_struct(cfg, precision, use_tensor_cores):
         c.pc_range[i] = cfg['pc_range'][i]
     c.precision = PRECISIONS[precision]
     c.use_tensor_cores = int(use_tensor_cores)
+    c.use_cams_embeds = int(cfg.get('use_cams_embeds', True))
+    rc = cfg.get('rotate_center', [100, 100])
+    c.rotate_center[0], c.rotate_center[1] = int(rc[0]), int(rc[1])
     return c
 
 
@@ -77,6 +80,17 @@ class OccEngine:
         cam, zs, h, w = camera_params(self.cfg, img_metas)
         _lib.check(self.lib.occb200_engine_set_cameras(self._h, _lib.ptr(cam), _lib.ptr(zs), h, w))
 
+    def _check_feats(self, feats, cuda):
+        """A mismatched tensor would be an out-of-bounds device read in the pack kernel: fail on the host instead."""
+        nc, C = self.cfg['num_cams'], self.cfg['embed_dims']
+        if len(feats) != self.cfg['num_levels']:
+            raise ValueError(f'expected {self.cfg["num_levels"]} feature levels, got {len(feats)}')
+        for l, (f, (h, w)) in enumerate(zip(feats, self.cfg['level_shapes'])):
+            if tuple(f.shape) != (nc, C, h, w):
+                raise ValueError(f'feature level {l}: shape {tuple(f.shape)} != configured {(nc, C, h, w)}')
+            if f.dtype != torch.float32 or f.is_cuda != cuda or not f.is_contiguous():
+                raise ValueError(f'feature level {l}: need a contiguous fp32 {"CUDA" if cuda else "CPU (pinned)"} tensor')
+
     def _feat_ptrs(self, feats):
         arr = (ctypes.c_void_p * 4)()
         for i, f in enumerate(feats):
@@ -89,8 +103,7 @@ class OccEngine:
         X, Y, Z = self.vox_shape
         dev = self.device
         feats = [f.contiguous() for f in feats]
-        for f in feats:
-            assert f.is_cuda and f.dtype == torch.float32 and f.dim() == 4
+        self._check_feats(feats, cuda=True)
         out = {}
         if 'bev_embed' in want:
             out['bev_embed'] = torch.empty((self.Nq, C), dtype=torch.float32, device=dev)
@@ -120,9 +133,9 @@ class OccEngine:
                 self._pinned = (torch.empty((X, Y, Z), dtype=torch.int64).pin_memory(),
                                 torch.empty((X, Y, Z, 2), dtype=torch.float32).pin_memory())
             occ_out, flow_out = self._pinned
+        self._check_feats(feats_host, cuda=False)
         arr = (ctypes.c_void_p * 4)()
         for i, f in enumerate(feats_host):
-            assert not f.is_cuda and f.dtype == torch.float32 and f.is_contiguous()
             arr[i] = f.data_ptr()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.occb200_engine_forward_host(self._h, arr, _lib.ptr(occ_out), _lib.ptr(flow_out),
@@ -131,9 +144,9 @@ class OccEngine:
 
     def submit_host(self, slot, feats_host, occ_out, flow_out):
         """Pipelined host-buffer call (slot 0/1): returns immediately; `wait_host(slot)` completes it."""
+        self._check_feats(feats_host, cuda=False)
         arr = (ctypes.c_void_p * 4)()
         for i, f in enumerate(feats_host):
-            assert not f.is_cuda and f.dtype == torch.float32 and f.is_contiguous()
             arr[i] = f.data_ptr()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.occb200_engine_submit_host(self._h, slot, arr, _lib.ptr(occ_out), _lib.ptr(flow_out),
@@ -167,9 +180,12 @@ class OccEngine:
         _lib.check(self.lib.occb200_engine_enable_taps(self._h, int(on)))
 
     def tap(self, which, layer=0):
-        names = {'layer': 0, 'tsa': 1, 'sca': 2, 'voxel': 3}
+        names = {'layer': 0, 'tsa': 1, 'sca': 2, 'voxel': 3, 'tokens': 4}
         w = names[which]
-        if w == 3:
+        if w == 4:
+            nv = sum(h * w_ for h, w_ in self.cfg['level_shapes'])
+            dst = torch.empty((self.cfg['num_cams'], nv, self.cfg['embed_dims']), dtype=torch.float32, device=self.device)
+        elif w == 3:
             X, Y, Z = self.vox_shape
             dst = torch.empty((X, Y, Z, self.cfg['out_dim']), dtype=torch.float32, device=self.device)
         else:

@@ -117,8 +117,18 @@ def render_forward(sigma, origin, points, tindex, grid, phase='test'):
     return [pred, gt, coord]
 
 
+def _no_autograd(name, *tensors):
+    """The module-level mirror is an INFERENCE path: these two building blocks have no backward.  Silently cutting the
+    graph would leave projection / FFN / norm weights without gradients, so a training-mode call fails loudly instead
+    (only `MultiScaleDeformableAttnFunction_fp32` is differentiable, as the reference's op is)."""
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise RuntimeError(f'occnet_b200.ops.{name}: no autograd support (inference path); wrap the call in '
+                           f'torch.no_grad() or detach the inputs')
+
+
 def linear(x, weight, bias=None, residual=None, act=0):
     """fp32 y = act(x W^T + b) (+ residual) through the CUDA-core GEMM (module-level API mirror)."""
+    _no_autograd('linear', x, weight, bias, residual)
     _require(x, 'x', torch.float32)
     _require(weight, 'weight', torch.float32)
     K = x.shape[-1]
@@ -134,6 +144,7 @@ def linear(x, weight, bias=None, residual=None, act=0):
 
 
 def layer_norm(x, gamma, beta):
+    _no_autograd('layer_norm', x, gamma, beta)
     _require(x, 'x', torch.float32)
     C = x.shape[-1]
     x2 = x.reshape(-1, C)

@@ -34,6 +34,22 @@ def _need_cuda(t, who):
         raise RuntimeError(f'{who}: CUDA tensors required (libocc_b200 has no CPU fallback)')
 
 
+def _inference_forward(fn):
+    """The stand-alone modules run their projections / norms / FFN through `ops.linear` / `ops.layer_norm`, which have no
+    backward: in eval mode the forward runs under `no_grad`; in training mode with autograd on it raises instead of
+    silently returning a graph that is cut at every projection (only the MSDA operator itself is differentiable)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kwargs):
+        if self.training and torch.is_grad_enabled():
+            raise RuntimeError(f'{type(self).__name__}: the libocc_b200 module mirror is an inference path (its linear / '
+                               f'norm building blocks have no autograd); call .eval() or use torch.no_grad()')
+        with torch.no_grad():
+            return fn(self, *args, **kwargs)
+    return wrapped
+
+
 def _offset_grid_bias(num_heads, num_levels, num_points):
     """Reference init of `sampling_offsets.bias`: head h looks along angle 2*pi*h/num_heads, point i at radius i+1."""
     thetas = torch.arange(num_heads, dtype=torch.float32) * (2.0 * math.pi / num_heads)
@@ -67,6 +83,7 @@ class MSDeformableAttention3D(BaseModule):
         xavier_init(self.value_proj, distribution='uniform', bias=0.)
         self._is_init = True
 
+    @_inference_forward
     def forward(self, query, key=None, value=None, identity=None, query_pos=None, key_padding_mask=None,
                 reference_points=None, spatial_shapes=None, level_start_index=None, **kwargs):
         _need_cuda(query, 'MSDeformableAttention3D')
@@ -116,6 +133,7 @@ class SpatialCrossAttention(BaseModule):
     def init_weight(self):
         xavier_init(self.output_proj, distribution='uniform', bias=0.)
 
+    @_inference_forward
     def forward(self, query, key, value, residual=None, query_pos=None, key_padding_mask=None, reference_points=None,
                 spatial_shapes=None, reference_points_cam=None, bev_mask=None, level_start_index=None, flag='encoder',
                 **kwargs):
@@ -168,6 +186,7 @@ class TemporalSelfAttention(BaseModule):
         xavier_init(self.output_proj, distribution='uniform', bias=0.)
         self._is_init = True
 
+    @_inference_forward
     def forward(self, query, key=None, value=None, identity=None, query_pos=None, key_padding_mask=None,
                 reference_points=None, spatial_shapes=None, level_start_index=None, flag='decoder', **kwargs):
         _need_cuda(query, 'TemporalSelfAttention')
@@ -266,6 +285,7 @@ class BEVFormerLayer(MyCustomBaseTransformerLayer):
         assert len(operation_order) == 6
         assert set(operation_order) == {'self_attn', 'norm', 'cross_attn', 'ffn'}
 
+    @_inference_forward
     def forward(self, query, key=None, value=None, bev_pos=None, query_pos=None, key_pos=None, attn_masks=None,
                 query_key_padding_mask=None, key_padding_mask=None, ref_2d=None, ref_3d=None, bev_h=None, bev_w=None,
                 reference_points_cam=None, mask=None, spatial_shapes=None, level_start_index=None, prev_bev=None,
@@ -339,6 +359,7 @@ class BEVFormerEncoder(TransformerLayerSequence):
         m = m & (xy[..., 1:2] > 0.0) & (xy[..., 1:2] < 1.0) & (xy[..., 0:1] < 1.0) & (xy[..., 0:1] > 0.0)
         return xy.permute(2, 1, 3, 0, 4), torch.nan_to_num(m).permute(2, 1, 3, 0, 4).squeeze(-1)
 
+    @_inference_forward
     def forward(self, bev_query, key, value, *args, bev_h=None, bev_w=None, bev_pos=None, spatial_shapes=None,
                 level_start_index=None, valid_ratios=None, prev_bev=None, **kwargs):
         _need_cuda(bev_query, 'BEVFormerEncoder')
@@ -374,7 +395,8 @@ def _engine_cfg(head):
                 num_layers=len(enc.layers), num_cams=t.num_cams, num_levels=da.num_levels,
                 num_points_in_pillar=enc.num_points_in_pillar, sca_points=da.num_points, tsa_points=tsa.num_points,
                 num_bev_queue=tsa.num_bev_queue, ffn_dim=lay.ffns[0].feedforward_channels, pillar_h=t.pillar_h,
-                out_dim=t.out_dim, num_classes=head.num_classes, pc_range=list(enc.pc_range))
+                out_dim=t.out_dim, num_classes=head.num_classes, pc_range=list(enc.pc_range),
+                use_cams_embeds=bool(t.use_cams_embeds), rotate_center=list(t.rotate_center))
 
 
 @TRANSFORMER.register_module()
@@ -475,23 +497,28 @@ class BEVFormerOccHead(BaseModule):
                 prev_bev = prev_bev.permute(1, 0, 2)
             if self.transformer.rotate_prev_bev:
                 prev_bev = self.transformer.rotate_prev(prev_bev, self.bev_h, self.bev_w, img_metas)
-        bevs, occs, flows = [], [], []
+        bevs, occs, flows, clss = [], [], [], []
         for b in range(bs):
             eng.set_cameras([img_metas[b] if b == 0 else dict(img_metas[b], ego2lidar=img_metas[0]['ego2lidar'],
                                                               img_shape=img_metas[0]['img_shape'])])
             out = eng.forward([f[b].float() for f in mlvl_feats], prev_bev=None if prev_bev is None else prev_bev[b],
-                              want=('bev_embed',) if only_bev else ('bev_embed', 'occ', 'flow'))
+                              want=('bev_embed',) if only_bev else ('bev_embed', 'occ', 'flow', 'occ_cls_i64'))
             bevs.append(out['bev_embed'])
             if not only_bev:
-                occs.append(out['occ']); flows.append(out['flow'])
+                occs.append(out['occ']); flows.append(out['flow']); clss.append(out['occ_cls_i64'])
         bev = torch.stack(bevs)                                               # (B, Nq, C)
         if only_bev:
             return bev
         bev_embed = bev.permute(0, 2, 1).reshape(bs, -1, self.bev_h, self.bev_w)
-        return {'bev_embed': bev_embed, 'occ': torch.stack(occs), 'flow': torch.stack(flows)}
+        # 'occ_cls' is the head kernel's fused argmax (int64, first-max tie rule like torch.argmax): `get_occ` returns it
+        # instead of re-reading the 43 MB of logits (reference: softmax(-1).argmax(-1), bevformer_occ_head.py:211-212)
+        return {'bev_embed': bev_embed, 'occ': torch.stack(occs), 'flow': torch.stack(flows), 'occ_cls': torch.stack(clss)}
 
     def get_occ(self, preds_dicts, img_metas, rescale=False):
-        return preds_dicts['occ'].argmax(-1), preds_dicts['flow']             # argmax(softmax(x)) == argmax(x)
+        cls = preds_dicts.get('occ_cls')
+        if cls is None:                                                       # a dict that did not come from forward()
+            cls = preds_dicts['occ'].argmax(-1)                               # argmax(softmax(x)) == argmax(x)
+        return cls, preds_dicts['flow']
 
 
 class _Bottleneck(nn.Module):

@@ -268,7 +268,8 @@ def pack_camera_features(p, prefix, cfg, mlvl_feats):
         bs, num_cam, c, h, w = feat.shape
         spatial_shapes.append((h, w))
         feat = feat.flatten(3).permute(1, 0, 3, 2)                               # (cam, B, hw, C)
-        feat = feat + p[prefix + '.cams_embeds'][:, None, None, :]
+        if cfg.get('use_cams_embeds', True):                                     # :214-215
+            feat = feat + p[prefix + '.cams_embeds'][:, None, None, :]
         feat = feat + p[prefix + '.level_embeds'][None, None, lvl:lvl + 1, :]
         feat_flatten.append(feat)
     feat_flatten = torch.cat(feat_flatten, 2)

@@ -20,15 +20,28 @@ def process_one_sample(sem_pred, lidar_rays, output_origin, flow_pred, device='c
     return pp.cpu().numpy()
 
 
-def main(sem_pred_list, sem_gt_list, flow_pred_list, flow_gt_list, lidar_origin_list, device='cuda:0', verbose=True):
+def main(sem_pred_list, sem_gt_list, flow_pred_list, flow_gt_list, lidar_origin_list, device='cuda:0', verbose=True,
+         distributed=False, count=None):
+    """reference `ray_metrics.main` (:200-257): same five lists, same returned scores.
+
+    The reference evaluates on rank 0 only with the full, de-duplicated result list (`tools/test.py:242`,
+    `apis/test.py:130`), so by default NO collective runs here (a rank-0-only call cannot hang an initialised
+    process group).  `distributed=True` is the sharded form: every rank passes the frames of its contiguous shard and
+    the 187 counters are SUM all-reduced; `count` (list of bool, default all True) marks the frames this rank owns
+    uniquely -- pass `occnet_b200.dist.owned_unique(...)`-derived flags so that the sampler's wrap-around padding
+    is not counted twice."""
     rm = RayMetric(device)
-    for sp, sg, fp, fg, orig in zip(sem_pred_list, sem_gt_list, flow_pred_list, flow_gt_list, lidar_origin_list):
+    for i, (sp, sg, fp, fg, orig) in enumerate(zip(sem_pred_list, sem_gt_list, flow_pred_list, flow_gt_list,
+                                                   lidar_origin_list)):
+        if count is not None and not count[i]:
+            continue
         sp = torch.as_tensor(np.reshape(sp, [200, 200, 16]).astype(np.uint8))
         sg = torch.as_tensor(np.reshape(sg, [200, 200, 16]).astype(np.uint8))
         fp = torch.as_tensor(np.reshape(fp, [200, 200, 16, 2]).astype(np.float32))
         fg = torch.as_tensor(np.reshape(fg, [200, 200, 16, 2]).astype(np.float32))
         rm.add_frame(sp, fp, sg, fg, torch.as_tensor(orig))
-    rm.all_reduce()
+    if distributed:
+        rm.all_reduce()
     fin = rm.finalize()
     if verbose:
         for i, name in enumerate(occ_class_names[:-1]):

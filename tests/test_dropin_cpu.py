@@ -100,6 +100,9 @@ def test_contiguous_shard_rule():
     got = [contiguous_shard(10, r, 4) for r in range(4)]                                    # ceil(10/4)=3, wrap-around pad
     assert got == [[0, 1, 2], [3, 4, 5], [6, 7, 8], [9, 0, 1]]
     assert contiguous_shard(0, 0, 2) == []
+    from occnet_b200.dist import owned_unique
+    assert [owned_unique(10, r, 4) for r in range(4)] == [[0, 1, 2], [0, 1, 2], [0, 1, 2], [0]]
+    assert sum(len(owned_unique(7, r, 8)) for r in range(8)) == 7 and owned_unique(8, 1, 2) == [0, 1, 2, 3]
     from projects.mmdet3d_plugin.datasets.samplers import DistributedSampler
     s = DistributedSampler(list(range(10)), num_replicas=4, rank=3, shuffle=False)
     assert list(iter(s)) == [9, 0, 1]
@@ -112,16 +115,18 @@ from occnet_b200 import dist as od, metric
 rank, local, world = od.init_from_env("gloo")
 assert world == 2 and dist.get_backend() == "gloo"
 frames = od.contiguous_shard(5, rank, world)
-# per-rank counters: a deterministic function of the frames this rank owns (stands in for the GPU metric kernel)
+own = od.owned_unique(5, rank, world)
+# per-rank counters: a deterministic function of the frames this rank owns (stands in for the GPU metric kernel).
+# 5 % 2 != 0: rank 1's shard is [3, 4, 0] -- frame 0 is wrap-around padding and must NOT be counted twice
+# (the reference truncates the collected results to len(dataset), apis/test.py:130).
 vec = torch.zeros(metric.NUM_COUNTERS, dtype=torch.float64)
-for f in frames:
-    rng = np.random.RandomState(f)
+for i in own:
+    rng = np.random.RandomState(frames[i])
     vec += torch.from_numpy(rng.randint(0, 50, metric.NUM_COUNTERS).astype(np.float64))
 od.all_reduce_counters(vec)
 want = torch.zeros_like(vec)
-for r in range(world):
-    for f in od.contiguous_shard(5, r, world):
-        want += torch.from_numpy(np.random.RandomState(f).randint(0, 50, metric.NUM_COUNTERS).astype(np.float64))
+for f in range(5):                                                  # single-rank counters over the 5 distinct frames
+    want += torch.from_numpy(np.random.RandomState(f).randint(0, 50, metric.NUM_COUNTERS).astype(np.float64))
 assert torch.equal(vec, want), (vec - want).abs().max()
 fin = metric.finalize_counters(vec.numpy())
 assert np.isnan(fin["ave"]).sum() == 8 or True

@@ -147,6 +147,28 @@ def test_pillar_projection_matches_point_sampling(base):
     assert d.max().item() < 1e-5                                 # normalised image coords of visible points
 
 
+# ------------------------------------------------------------------------------------------ feature packing (a9)
+@pytest.mark.parametrize('precision,use_cams', [('fp32', True), ('fp32', False), ('bf16', True)])
+def test_pack_levels_matches_get_bev_features(precision, use_cams):
+    """transformer_occ.py:207-227 on its own: NCHW levels -> (cam, Nv, C) tokens + cams_embeds (if enabled) + level_embeds.
+    fp32: bit-exact (same two additions in the same order); bf16 storage: the fp32 result rounded once."""
+    O, _, _ = _oracle()
+    cfg, params, feats, metas, _ = make_case('small6', num_layers=1, use_cams_embeds=use_cams)
+    eng = engine_for(cfg, params, metas, precision)
+    eng.forward([f[0].to(DEV) for f in feats], want=('bev_embed',))
+    got = eng.tap('tokens').cpu()
+    want, shapes, lsi = O.pack_camera_features(params, 'transformer', cfg, feats)       # (cam, Nv, B, C)
+    want = want[:, :, 0]
+    assert lsi.tolist() == [0] + np.cumsum([h * w for h, w in cfg['level_shapes']])[:-1].tolist()
+    if precision == 'fp32':
+        assert torch.equal(got, want)
+    else:
+        assert torch.equal(got, want.bfloat16().float())
+    if not use_cams:                                             # the embedding really is off (and on in the default case)
+        with_cams, _, _ = O.pack_camera_features(params, 'transformer', dict(cfg, use_cams_embeds=True), feats)
+        assert not torch.equal(got, with_cams[:, :, 0])
+
+
 # ------------------------------------------------------------------------------------------ full path, fp32 config
 def _check_fp32(cfg, params, feats, metas, prev, per_layer=True):
     O, _, _ = _oracle()
@@ -545,7 +567,7 @@ def test_plugin_detector_output_contract():
     assert set(out) == {'occ_results', 'flow_results'}
     assert out['occ_results'].dtype == torch.int64 and not out['occ_results'].is_cuda
     assert tuple(out['occ_results'].shape) == (1, 40, 40, 16) and tuple(out['flow_results'].shape) == (1, 40, 40, 16, 2)
-    with pytest.raises(RuntimeError, match='no image backbone'):
+    with pytest.raises(RuntimeError, match='pass img_feats'):
         det(return_loss=False, img=[torch.zeros(1, 6, 3, 64, 64, device=DEV)], img_metas=[metas])
 
 
