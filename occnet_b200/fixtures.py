@@ -115,10 +115,16 @@ def make_ray_origins(T=8, z=1.84):
     return o[None]
 
 
-def init_params(cfg, seed=2, perturb=True, num_embed_levels=None):
+FREE_BIAS = 1.25      # see init_params(free_bias=...)
+
+
+def init_params(cfg, seed=2, perturb=True, num_embed_levels=None, free_bias=0.0):
     """Reference `init_weights` (spatial_cross_attention.py:253-271, temporal_self_attention.py:107-126,
     transformer_occ.py:154-167) followed by the SURVEY 8d perturbation so that offsets / weights are
-    query-dependent (the stock init zeroes `sampling_offsets.weight` and `attention_weights.weight`)."""
+    query-dependent (the stock init zeroes `sampling_offsets.weight` and `attention_weights.weight`).
+    `free_bias` is added to the bias of the 'free' class (index num_classes-1) of the semantic head: with purely random
+    weights only ~1 % of the voxels come out free, every metric ray then stops in its first voxel and Ray-mIoU is
+    degenerate; FREE_BIAS = 1.25 makes ~78 % of the full-size fixture's voxels free (rays travel, classes compete)."""
     g = torch.Generator().manual_seed(seed)
     C = cfg['embed_dims']; M = cfg['num_heads']; L = cfg['num_levels']; P = cfg['sca_points']
     Pt = cfg['tsa_points']; Q = cfg['num_bev_queue']; F_ = cfg['ffn_dim']
@@ -180,6 +186,8 @@ def init_params(cfg, seed=2, perturb=True, num_embed_levels=None):
         p[f'transformer.{name}.0.bias'] = torch.randn(od * 2, generator=g) * 0.05
         p[f'transformer.{name}.2.weight'] = xavier(out, od * 2)
         p[f'transformer.{name}.2.bias'] = torch.randn(out, generator=g) * 0.05
+    if free_bias:
+        p['transformer.predicter.2.bias'][cfg['num_classes'] - 1] += free_bias
     return p
 
 

@@ -482,6 +482,148 @@ def test_full_size_properties_bf16(tc):
         assert (a['occ_cls'] == ref['occ_cls']).float().mean().item() > 0.97
 
 
+
+# ------------------------------------------------------------------------------------------ FULL SIZE, 6 LAYERS (goldens)
+def _report(name, vals):
+    """Measured parity numbers of this run -> gpurun_out/parity_report.json (evidence; copied to profiles/)."""
+    import json
+    d = os.path.join(ROOT, 'gpurun_out')
+    os.makedirs(d, exist_ok=True)
+    path = os.path.join(d, 'parity_report.json')
+    rep = json.load(open(path)) if os.path.exists(path) else {}
+    rep[name] = {k: (float(v) if not isinstance(v, (str, list)) else v) for k, v in vals.items()}
+    json.dump(rep, open(path, 'w'), indent=1)
+
+
+def _full6_case(prev=False):
+    sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
+    cfg = fixtures.make_cfg('full', num_layers=6)
+    params = fixtures.init_params(cfg, seed=2, free_bias=fixtures.FREE_BIAS)
+    feats = fixtures.make_feats(cfg, bs=1, seed=100)
+    metas = fixtures.make_img_metas(cfg, bs=1, can_bus_angle=3.0 if prev else None)
+    pb = None
+    if prev:
+        O, _, _ = _oracle()
+        pb = torch.randn(1, cfg['bev_h'] * cfg['bev_w'], cfg['embed_dims'], generator=torch.Generator().manual_seed(3))
+        pb = O.rotate_prev_bev(pb[0], cfg['bev_h'], cfg['bev_w'], 3.0, cfg.get('rotate_center', [100, 100]))[None]
+    return cfg, params, feats, metas, pb
+
+
+def _sub_err(key, t, golden, n):
+    from sampling import sub_idx
+    flat = t.reshape(-1).cpu()
+    got = flat[torch.from_numpy(sub_idx(key, flat.numel(), n))].numpy()
+    d = np.abs(got - golden[key + '_sub'])
+    return float(d.max()), float(d.mean())
+
+
+def _ray_miou_vs(pred_cls, pred_flow, gt_cls, gt_flow):
+    """Ray-mIoU / mAVE of a prediction with ANOTHER prediction standing in as ground truth (parity as the metric sees it)."""
+    from occnet_b200 import metric
+    rm = metric.RayMetric(DEV)
+    rm.add_frame(pred_cls, pred_flow, gt_cls, gt_flow, torch.from_numpy(fixtures.make_ray_origins(T=8)))
+    return rm.finalize()
+
+
+def _ray_counters_vs_scene(pred_cls, pred_flow):
+    from occnet_b200 import metric
+    sem_gt, flow_gt = fixtures.make_occ_scene(seed=4)
+    rm = metric.RayMetric(DEV)
+    rm.add_frame(pred_cls, pred_flow, torch.from_numpy(sem_gt), torch.from_numpy(flow_gt),
+                 torch.from_numpy(fixtures.make_ray_origins(T=8)))
+    return rm.counters.cpu().numpy()
+
+
+def test_full_size_six_layers_fp32_vs_oracle_golden(golden_dir):
+    """BASELINE configs[1]: 6 x 928x1600 -> 200x200 BEV, SIX encoder layers, voxel decoder, heads, fp32 configuration.
+    Every per-layer tap and every output within 1e-3 of the oracle (golden: tests/golden/gen_fullsize.py, oracle pinned
+    bit-exactly to the reference modules); class volume and Ray-mIoU counters as the reference's metric sees them."""
+    from sampling import N_OUT, N_TAP
+    cfg, params, feats, metas, _ = _full6_case()
+    g = np.load(os.path.join(golden_dir, 'full6_fp32.npz'))
+    eng = engine_for(cfg, params, metas, 'fp32')
+    eng.enable_taps(True)
+    out = eng.forward([f[0].to(DEV) for f in feats], want=('bev_embed', 'occ', 'flow', 'occ_cls'))
+    torch.cuda.synchronize()
+    rep = {}
+    for l in range(6):
+        for name in ('tsa', 'sca', 'layer'):
+            key = f'layer{l}' + ('' if name == 'layer' else '_' + name)
+            mx, _ = _sub_err(key, eng.tap(name, l), g, N_TAP)
+            rep[key] = mx
+            assert mx < 1e-3, f'{key}: {mx}'
+    bev, occ, flow = to_ref_layout(out, cfg)
+    for key, t in (('bev_embed', bev), ('voxel', eng.tap('voxel')), ('occ', occ), ('flow', flow)):
+        mx, mean = _sub_err(key, t, g, N_OUT)
+        rep[key] = mx
+        assert mx < 1e-3, f'{key}: {mx}'
+    cls_g = torch.from_numpy(g['occ_cls'])
+    agree = (out['occ_cls'].cpu() == cls_g).float().mean().item()
+    assert agree > 0.9995                                        # logits within 1e-3: only near-ties may flip
+    fin = _ray_miou_vs(out['occ_cls'], out['flow'], cls_g, torch.from_numpy(g['flow_f16'].astype(np.float32)))
+    rep.update(class_agreement=agree, ray_miou_vs_oracle_output=fin['miou'], ray_mave_vs_oracle_output=fin['mave'])
+    assert fin['miou'] > 0.995, fin['miou']                      # Ray-mIoU of the CUDA output scored against the oracle's
+    cnt = _ray_counters_vs_scene(out['occ_cls'], out['flow'])
+    n = 17                                                       # integer counters vs the synthetic GT scene
+    rel = np.abs(cnt[:5 * n] - g['counters'][:5 * n]).sum() / max(g['counters'][:5 * n].sum(), 1)
+    rep['counter_rel_diff_vs_oracle_counters'] = rel
+    assert rel < 2e-3, rel
+    _report('full6_fp32', rep)
+
+
+def _check_full6_bf16(prev, golden_dir):
+    from sampling import N_OUT
+    tag = 'full6_prev' if prev else 'full6'
+    cfg, params, feats, metas, pb = _full6_case(prev)
+    g32 = np.load(os.path.join(golden_dir, f'{tag}_fp32.npz'))
+    g16 = np.load(os.path.join(golden_dir, f'{tag}_bf16.npz'))
+    eng = engine_for(cfg, params, metas, 'bf16', tc=True)        # NO taps: the fused configuration bench.py times
+    out = eng.forward([f[0].to(DEV) for f in feats], prev_bev=pb, want=('bev_embed', 'occ', 'flow', 'occ_cls'))
+    torch.cuda.synchronize()
+    bev, occ, flow = to_ref_layout(out, cfg)
+    rep = {}
+    for key, t in (('bev_embed', bev), ('voxel', eng.tap('voxel')), ('occ', occ), ('flow', flow)):
+        rep[key + '_max_vs_bf16_model'], rep[key + '_mean_vs_bf16_model'] = _sub_err(key, t, g16, N_OUT)
+        if key != 'voxel':
+            rep[key + '_max_vs_fp32_oracle'], rep[key + '_mean_vs_fp32_oracle'] = _sub_err(key, t, g32, N_OUT)
+    cls32, cls16 = torch.from_numpy(g32['occ_cls']), torch.from_numpy(g16['occ_cls'])
+    rep['class_agreement_vs_fp32_oracle'] = (out['occ_cls'].cpu() == cls32).float().mean().item()
+    rep['class_agreement_vs_bf16_model'] = (out['occ_cls'].cpu() == cls16).float().mean().item()
+    fin16 = _ray_miou_vs(out['occ_cls'], out['flow'], cls16, out['flow'])
+    fin32 = _ray_miou_vs(out['occ_cls'], out['flow'], cls32, out['flow'])
+    rep['ray_miou_vs_bf16_model_output'], rep['ray_miou_vs_fp32_oracle_output'] = fin16['miou'], fin32['miou']
+    _report(tag + '_bf16_tc', rep)
+    # (i) against the fp32 oracle: what 8-bit mantissas allow (the storage-rounding MODEL itself sits at 3.3e-2 / 3.8e-3)
+    for key in ('bev_embed', 'occ', 'flow'):
+        assert rep[key + '_max_vs_fp32_oracle'] < 6e-2, (key, rep)
+        assert rep[key + '_mean_vs_fp32_oracle'] < 6e-3, (key, rep)
+    assert rep['class_agreement_vs_fp32_oracle'] > 0.99, rep
+    # (ii) against the same algorithm rounded at the engine's storage points: tight
+    for key in ('bev_embed', 'occ', 'flow'):
+        assert rep[key + '_max_vs_bf16_model'] < BF16_MODEL_TOL_MAX, (key, rep)
+        assert rep[key + '_mean_vs_bf16_model'] < BF16_MODEL_TOL_MEAN, (key, rep)
+    assert rep['voxel_mean_vs_bf16_model'] < BF16_MODEL_TOL_MEAN, rep          # bf16 tensor: max = one ulp flip (2^-7 |v|)
+    assert rep['class_agreement_vs_bf16_model'] > 0.999, rep
+    assert rep['ray_miou_vs_bf16_model_output'] > 0.99 and rep['ray_miou_vs_fp32_oracle_output'] > 0.9, rep
+    return rep
+
+
+BF16_MODEL_TOL_MAX, BF16_MODEL_TOL_MEAN = 8e-3, 4e-4
+
+
+def test_full_size_six_layers_bf16_tensor_cores_vs_goldens(golden_dir):
+    """The configuration bench.py times (bf16 storage, tcgen05 GEMM / conv / heads, fused LayerNorm epilogues, hoisted
+    value_proj, folded TSA projection, fp16 sampling projections) at FULL size, SIX layers, against (i) the fp32 oracle
+    and (ii) the storage-rounding model of the same algorithm (oracle/bf16_model.py)."""
+    _check_full6_bf16(False, golden_dir)
+
+
+def test_full_size_six_layers_bf16_temporal_prev_bev(golden_dir):
+    """Same with a previous BEV (BASELINE configs[2]: TemporalSelfAttention over [prev_bev, current]): the has_prev branch
+    of the fused path (unfolded query projection over prev_t / q+pos, q+pos written by the FFN LayerNorm epilogue)."""
+    _check_full6_bf16(True, golden_dir)
+
+
 # ------------------------------------------------------------------------------------------ drop-in module API
 def _plugin_head(cfg, params, precision='fp32'):
     import projects.mmdet3d_plugin  # noqa: F401
