@@ -96,6 +96,11 @@ int occb200_engine_finalize(occb200_engine* e);
  * img_metas[0]['img_shape'][0][:2] (encoder.py:133-134). */
 int occb200_engine_set_cameras(occb200_engine* e, const float* cam_mat, const float* zs, int img_h, int img_w);
 
+/* Element type of the feature levels handed to _forward / _forward_host / _submit_host from now on: 0 = fp32 (default,
+ * the reference's dtype), 1 = bf16 (same [num_cams, C, h, w] layout, pointers passed through the same arguments): what
+ * an on-device backbone emits, and half the PCIe bytes for host pipelines that already hold bf16 features. */
+int occb200_engine_set_input_dtype(occb200_engine* e, int feats_bf16);
+
 /* One frame, DEVICE buffers.
  *   feats[l]   dev f32 [num_cams, C, h_l, w_l]  (FPN outputs of one batch item, NCHW)
  *   prev_bev   dev f32 [Nq, C] or NULL          (already rotated; NULL = the reference's only runtime mode)

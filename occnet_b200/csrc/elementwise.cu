@@ -10,7 +10,7 @@ namespace {
 // [cam][C][hw] f32 -> [cam][Nv][C] T (+ cams_embeds[cam][c], then + level_embed[c]; same order as the reference).
 // 64 (pixels) x 64 (channels) tile per CTA: float4 reads along the pixel axis, 16-byte (8 x bf16) writes along C.
 // All FPN levels in one launch: blockIdx.x walks the 64-pixel tiles of level 0, then level 1, ...
-template <typename T>
+template <typename T, typename TI>
 __global__ void __launch_bounds__(256)
 pack_levels_kernel(PackLevels pl, const float* __restrict__ cams_embeds, const float* __restrict__ level_embeds, int C,
                    int Nv, T* __restrict__ tokens)
@@ -19,30 +19,49 @@ pack_levels_kernel(PackLevels pl, const float* __restrict__ cams_embeds, const f
     int lvl = 0;
 #pragma unroll
     for (int l = 1; l < 8; ++l) if (l < pl.num_levels && (int)blockIdx.x >= pl.tile_begin[l]) lvl = l;
-    const float* feat = nullptr; int hw = 0, start = 0, tb = 0;
+    const void* feat_v = nullptr; int hw = 0, start = 0, tb = 0;
 #pragma unroll
     for (int l = 0; l < 8; ++l)                                // static selects (no dynamically indexed parameter copy)
-        if (l == lvl) { feat = pl.feat[l]; hw = pl.hw[l]; start = pl.start[l]; tb = pl.tile_begin[l]; }
+        if (l == lvl) { feat_v = pl.feat[l]; hw = pl.hw[l]; start = pl.start[l]; tb = pl.tile_begin[l]; }
+    const TI* feat = reinterpret_cast<const TI*>(feat_v);
     const float* level_embed = level_embeds + lvl * C;
     const int cam = blockIdx.z;
     const int p0 = ((int)blockIdx.x - tb) * 64, c0 = blockIdx.y * 64;
     const int tid = threadIdx.x;
-    const float* src = feat + (int64_t)cam * C * hw;
-    const bool vec_ok = (hw & 3) == 0;
+    const TI* src = feat + (int64_t)cam * C * hw;
+    if constexpr (sizeof(TI) == 4) {
+        const bool vec_ok = (hw & 3) == 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {                              // 64 channels x 16 float4 = 1024 float4, 4 per thread
-        const int idx = tid + i * 256;
-        const int c = idx >> 4, p4 = (idx & 15) * 4;
-        const float* sp = src + (int64_t)(c0 + c) * hw + p0 + p4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (vec_ok && p0 + p4 + 3 < hw) v = __ldg(reinterpret_cast<const float4*>(sp));
-        else {
-            if (p0 + p4 + 0 < hw) v.x = __ldg(sp + 0);
-            if (p0 + p4 + 1 < hw) v.y = __ldg(sp + 1);
-            if (p0 + p4 + 2 < hw) v.z = __ldg(sp + 2);
-            if (p0 + p4 + 3 < hw) v.w = __ldg(sp + 3);
+        for (int i = 0; i < 4; ++i) {                          // 64 channels x 16 float4 = 1024 float4, 4 per thread
+            const int idx = tid + i * 256;
+            const int c = idx >> 4, p4 = (idx & 15) * 4;
+            const float* sp = src + (int64_t)(c0 + c) * hw + p0 + p4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (vec_ok && p0 + p4 + 3 < hw) v = __ldg(reinterpret_cast<const float4*>(sp));
+            else {
+                if (p0 + p4 + 0 < hw) v.x = __ldg(sp + 0);
+                if (p0 + p4 + 1 < hw) v.y = __ldg(sp + 1);
+                if (p0 + p4 + 2 < hw) v.z = __ldg(sp + 2);
+                if (p0 + p4 + 3 < hw) v.w = __ldg(sp + 3);
+            }
+            tile[c][p4 + 0] = v.x; tile[c][p4 + 1] = v.y; tile[c][p4 + 2] = v.z; tile[c][p4 + 3] = v.w;
         }
-        tile[c][p4 + 0] = v.x; tile[c][p4 + 1] = v.y; tile[c][p4 + 2] = v.z; tile[c][p4 + 3] = v.w;
+    } else {                                                   // bf16 features (what an on-device backbone hands over)
+        const bool vec_ok = (hw & 7) == 0;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {                          // 64 channels x 8 uint4 (8 pixels each), 2 per thread
+            const int idx = tid + i * 256;
+            const int c = idx >> 3, p8 = (idx & 7) * 8;
+            const bf16* sp = src + (int64_t)(c0 + c) * hw + p0 + p8;
+            float v[8];
+            if (vec_ok && p0 + p8 + 7 < hw) load8(sp, v);
+            else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = (p0 + p8 + k < hw) ? __bfloat162float(sp[k]) : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) tile[c][p8 + k] = v[k];
+        }
     }
     __syncthreads();
 #pragma unroll
@@ -165,8 +184,8 @@ __global__ void cast_kernel(const float* __restrict__ s, T* __restrict__ d, int6
 }  // namespace
 
 template <typename T>
-int launch_pack_levels(const float* const* feats, const LevelGeom& lg, const float* cams_embeds, const float* level_embeds,
-                       int num_cams, int C, int Nv, T* tokens, cudaStream_t stream)
+int launch_pack_levels(const void* const* feats, int feats_bf16, const LevelGeom& lg, const float* cams_embeds,
+                       const float* level_embeds, int num_cams, int C, int Nv, T* tokens, cudaStream_t stream)
 {
     OCC_CHECK(C % 64 == 0, "pack_levels: C must be a multiple of 64");
     OCC_CHECK(lg.num_levels >= 1 && lg.num_levels <= 8, "pack_levels: 1..8 levels");
@@ -178,13 +197,14 @@ int launch_pack_levels(const float* const* feats, const LevelGeom& lg, const flo
         tiles += ceil_div(pl.hw[l], 64);
     }
     dim3 grid(tiles, C / 64, num_cams);
-    pack_levels_kernel<T><<<grid, 256, 0, stream>>>(pl, cams_embeds, level_embeds, C, Nv, tokens);
+    if (feats_bf16) pack_levels_kernel<T, bf16><<<grid, 256, 0, stream>>>(pl, cams_embeds, level_embeds, C, Nv, tokens);
+    else            pack_levels_kernel<T, float><<<grid, 256, 0, stream>>>(pl, cams_embeds, level_embeds, C, Nv, tokens);
     OCC_CUDA(cudaGetLastError());
     return 0;
 }
-template int launch_pack_levels<float>(const float* const*, const LevelGeom&, const float*, const float*, int, int, int,
+template int launch_pack_levels<float>(const void* const*, int, const LevelGeom&, const float*, const float*, int, int, int,
                                        float*, cudaStream_t);
-template int launch_pack_levels<bf16>(const float* const*, const LevelGeom&, const float*, const float*, int, int, int,
+template int launch_pack_levels<bf16>(const void* const*, int, const LevelGeom&, const float*, const float*, int, int, int,
                                       bf16*, cudaStream_t);
 
 template <typename T>

@@ -63,6 +63,7 @@ struct occb200_engine {
     LevelGeom lg;
     ScaParams sp;
     bool cameras_set = false, finalized = false, taps = false;
+    int feats_bf16 = 0;                 // occb200_engine_set_input_dtype: feature levels arrive as bf16 instead of fp32
     std::map<std::string, std::vector<float>> host_params;
     std::vector<LayerW> layers;
     DevBuf bev_queries, pos, pos_t32, cams_embeds, level_embeds;
@@ -187,8 +188,8 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
     T* tokens = e->tokens.as<T>();
     {
         ProfScope ps(e, st, CAT_PACK);
-        if (launch_pack_levels<T>(feats, e->lg, e->cams_embeds.as<float>(), e->level_embeds.as<float>(), ncam, C, Nv, tokens,
-                                  st)) return 2;
+        if (launch_pack_levels<T>(reinterpret_cast<const void* const*>(feats), e->feats_bf16, e->lg, e->cams_embeds.as<float>(),
+                                  e->level_embeds.as<float>(), ncam, C, Nv, tokens, st)) return 2;
         e->launches++;
     }
     float* q_f32 = e->q_f32.as<float>();
@@ -747,7 +748,7 @@ int occb200_engine_forward_host(occb200_engine* e, const float* const* feats_hos
     const size_t nvox = (size_t)c.bev_w * c.bev_h * c.pillar_h;
     const float* dev_feats[4];
     for (int l = 0; l < 4; ++l) {
-        const size_t n = (size_t)c.num_cams * 256 * e->lg.h[l] * e->lg.w[l] * 4;
+        const size_t n = (size_t)c.num_cams * 256 * e->lg.h[l] * e->lg.w[l] * (e->feats_bf16 ? 2 : 4);
         if (e->feats_dev[l].bytes != n && e->feats_dev[l].alloc(n)) return 2;
         OCC_CUDA(cudaMemcpyAsync(e->feats_dev[l].p, feats_host[l], n, cudaMemcpyHostToDevice, st));
         dev_feats[l] = e->feats_dev[l].as<float>();
@@ -792,7 +793,7 @@ int occb200_engine_submit_host(occb200_engine* e, int slot, const float* const* 
     const size_t nvox = (size_t)c.bev_w * c.bev_h * c.pillar_h;
     const float* dev_feats[4];
     for (int l = 0; l < 4; ++l) {
-        const size_t n = (size_t)c.num_cams * 256 * e->lg.h[l] * e->lg.w[l] * 4;
+        const size_t n = (size_t)c.num_cams * 256 * e->lg.h[l] * e->lg.w[l] * (e->feats_bf16 ? 2 : 4);
         if (s.feats[l].bytes != n && s.feats[l].alloc(n)) return 2;
         const int pieces = n >= (32u << 20) ? nsplit : 1;
         const size_t chunk = ((n / pieces) + 255) & ~(size_t)255;
@@ -828,6 +829,13 @@ int occb200_engine_wait_host(occb200_engine* e, int slot)
     if (!s.busy) return 0;
     OCC_CUDA(cudaEventSynchronize(s.d2h_done));
     s.busy = false;
+    return 0;
+}
+
+int occb200_engine_set_input_dtype(occb200_engine* e, int feats_bf16)
+{
+    OCC_CHECK(e && (feats_bf16 == 0 || feats_bf16 == 1), "input dtype must be 0 (fp32) or 1 (bf16)");
+    e->feats_bf16 = feats_bf16;
     return 0;
 }
 

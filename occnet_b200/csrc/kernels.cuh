@@ -43,10 +43,11 @@ template <typename T> int launch_nhwc_to_nchw_f32(const T* src, float* dst, int 
 // ---- elementwise.cu
 // feats level l: [num_cams, C, h, w] f32 (NCHW) -> tokens [num_cams, Nv, C] T, + cams_embeds + level_embeds
 // (all levels in one launch; level_embeds [num_levels, C])
-struct PackLevels { const float* feat[8]; int hw[8], start[8], tile_begin[8], num_levels; };
+// `feats_bf16` != 0: the levels are bf16 [num_cams, C, h, w] (what an on-device backbone / a bf16 host pipeline hands over)
+struct PackLevels { const void* feat[8]; int hw[8], start[8], tile_begin[8], num_levels; };
 template <typename T>
-int launch_pack_levels(const float* const* feats, const LevelGeom& lg, const float* cams_embeds, const float* level_embeds,
-                       int num_cams, int C, int Nv, T* tokens, cudaStream_t stream);
+int launch_pack_levels(const void* const* feats, int feats_bf16, const LevelGeom& lg, const float* cams_embeds,
+                       const float* level_embeds, int num_cams, int C, int Nv, T* tokens, cudaStream_t stream);
 // y = LayerNorm(x) (eps 1e-5); writes fp32 copy (residual stream), T copy (GEMM operand) and T copy of y + pos
 template <typename T>
 int launch_layernorm(const float* x, const float* gamma, const float* beta, const float* pos, int rows, int C,

@@ -69,6 +69,13 @@ class OccEngine:
         self.Nq = cfg['bev_h'] * cfg['bev_w']
         self.vox_shape = (cfg['bev_w'], cfg['bev_h'], cfg['pillar_h'])
         self._pinned = None
+        self.feat_dtype = torch.float32
+
+    def set_input_dtype(self, dtype):
+        """Feature levels are handed over as `dtype` from now on (torch.float32, the reference's, or torch.bfloat16)."""
+        assert dtype in (torch.float32, torch.bfloat16)
+        _lib.check(self.lib.occb200_engine_set_input_dtype(self._h, int(dtype == torch.bfloat16)))
+        self.feat_dtype = dtype
 
     def __del__(self):
         h = getattr(self, '_h', None)
@@ -88,8 +95,8 @@ class OccEngine:
         for l, (f, (h, w)) in enumerate(zip(feats, self.cfg['level_shapes'])):
             if tuple(f.shape) != (nc, C, h, w):
                 raise ValueError(f'feature level {l}: shape {tuple(f.shape)} != configured {(nc, C, h, w)}')
-            if f.dtype != torch.float32 or f.is_cuda != cuda or not f.is_contiguous():
-                raise ValueError(f'feature level {l}: need a contiguous fp32 {"CUDA" if cuda else "CPU (pinned)"} tensor')
+            if f.dtype != self.feat_dtype or f.is_cuda != cuda or not f.is_contiguous():
+                raise ValueError(f'feature level {l}: need a contiguous {self.feat_dtype} {"CUDA" if cuda else "CPU (pinned)"} tensor')
 
     def _feat_ptrs(self, feats):
         arr = (ctypes.c_void_p * 4)()

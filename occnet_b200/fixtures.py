@@ -235,3 +235,31 @@ def init_backbone_params(seed=5, out_channels=256, bn_stats=True):
         p[f'{nk}fpn_convs.{i}.conv.weight'] = (torch.rand(out_channels, out_channels, 3, 3, generator=g) * 2 - 1) * bound
         p[f'{nk}fpn_convs.{i}.conv.bias'] = 0.05 * torch.randn(out_channels, generator=g)
     return p
+
+
+def head_cfg(cfg):
+    """mmcv-style config dict of `BEVFormerOccHead` (same keys as bevformer_base_occ.py:67-135) for a fixture geometry."""
+    C = cfg['embed_dims']
+    return dict(
+        type='BEVFormerOccHead', pc_range=cfg['pc_range'], bev_h=cfg['bev_h'], bev_w=cfg['bev_w'],
+        num_classes=cfg['num_classes'], in_channels=C, sync_cls_avg_factor=True, with_box_refine=True, as_two_stage=False,
+        use_mask=False, loss_occ=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0),
+        loss_flow=dict(type='L1Loss', loss_weight=0.25),
+        transformer=dict(
+            type='TransformerOcc', pillar_h=cfg['pillar_h'], num_classes=cfg['num_classes'], norm_cfg=dict(type='BN'),
+            norm_cfg_3d=dict(type='BN3d'), use_3d=True, use_conv=False, rotate_prev_bev=True, use_shift=True,
+            use_can_bus=True, embed_dims=C, num_cams=cfg['num_cams'], rotate_center=cfg.get('rotate_center', [100, 100]),
+            encoder=dict(
+                type='BEVFormerEncoder', num_layers=cfg['num_layers'], pc_range=cfg['pc_range'],
+                num_points_in_pillar=cfg['num_points_in_pillar'], return_intermediate=False,
+                transformerlayers=dict(
+                    type='BEVFormerLayer',
+                    attn_cfgs=[dict(type='TemporalSelfAttention', embed_dims=C, num_levels=1),
+                               dict(type='SpatialCrossAttention', pc_range=cfg['pc_range'], num_cams=cfg['num_cams'],
+                                    deformable_attention=dict(type='MSDeformableAttention3D', embed_dims=C,
+                                                              num_points=cfg['sca_points'], num_levels=cfg['num_levels']),
+                                    embed_dims=C)],
+                    feedforward_channels=cfg['ffn_dim'], ffn_dropout=0.1,
+                    operation_order=('self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm')))),
+        positional_encoding=dict(type='LearnedPositionalEncoding', num_feats=C // 2, row_num_embed=cfg['bev_h'],
+                                 col_num_embed=cfg['bev_w']))

@@ -457,7 +457,7 @@ class BEVFormerOccHead(BaseModule):
     def __init__(self, *args, with_box_refine=False, as_two_stage=False, transformer=None, bbox_coder=None,
                  num_cls_fcs=2, code_weights=None, pc_range=[-40, -40, -1.0, 40, 40, 5.4], bev_h=30, bev_w=30,
                  loss_occ=None, loss_flow=None, use_mask=False, positional_encoding=None, precision='fp32',
-                 use_tensor_cores=None, **kwargs):
+                 use_tensor_cores=None, test_logits=True, **kwargs):
         super().__init__()
         self.bev_h, self.bev_w, self.num_classes, self.use_mask = bev_h, bev_w, kwargs['num_classes'], use_mask
         self.with_box_refine, self.as_two_stage, self.pc_range = with_box_refine, as_two_stage, pc_range
@@ -470,6 +470,9 @@ class BEVFormerOccHead(BaseModule):
         self.bev_embedding = nn.Embedding(bev_h * bev_w, self.embed_dims)
         self.precision = precision                       # 'fp32' (reference arithmetic) or 'bf16' (throughput config)
         self.use_tensor_cores = (precision == 'bf16') if use_tensor_cores is None else use_tensor_cores
+        # test_logits=False: `forward(test=True)` (the detector's inference call) does not materialise the 43 MB of fp32
+        # semantic logits -- `get_occ` only needs their argmax, which the head kernel emits fused ('occ' is then None)
+        self.test_logits = test_logits
         self._engine, self._engine_key = None, None
 
     def init_weights(self):
@@ -498,21 +501,31 @@ class BEVFormerOccHead(BaseModule):
             if self.transformer.rotate_prev_bev:
                 prev_bev = self.transformer.rotate_prev(prev_bev, self.bev_h, self.bev_w, img_metas)
         bevs, occs, flows, clss = [], [], [], []
+        want = ('bev_embed', 'occ', 'flow', 'occ_cls_i64') if (self.test_logits or not test) else ('bev_embed', 'flow', 'occ_cls_i64')
         for b in range(bs):
             eng.set_cameras([img_metas[b] if b == 0 else dict(img_metas[b], ego2lidar=img_metas[0]['ego2lidar'],
                                                               img_shape=img_metas[0]['img_shape'])])
-            out = eng.forward([f[b].float() for f in mlvl_feats], prev_bev=None if prev_bev is None else prev_bev[b],
-                              want=('bev_embed',) if only_bev else ('bev_embed', 'occ', 'flow', 'occ_cls_i64'))
+            fb = [f[b] for f in mlvl_feats]
+            if fb[0].dtype != eng.feat_dtype:                                 # fp32 (reference dtype) or bf16 features
+                if fb[0].dtype == torch.bfloat16 or eng.feat_dtype == torch.bfloat16:
+                    eng.set_input_dtype(torch.bfloat16 if fb[0].dtype == torch.bfloat16 else torch.float32)
+                if fb[0].dtype != eng.feat_dtype:
+                    fb = [f.float() for f in fb]
+            out = eng.forward(fb, prev_bev=None if prev_bev is None else prev_bev[b],
+                              want=('bev_embed',) if only_bev else want)
             bevs.append(out['bev_embed'])
             if not only_bev:
-                occs.append(out['occ']); flows.append(out['flow']); clss.append(out['occ_cls_i64'])
+                flows.append(out['flow']); clss.append(out['occ_cls_i64'])
+                if 'occ' in out:
+                    occs.append(out['occ'])
         bev = torch.stack(bevs)                                               # (B, Nq, C)
         if only_bev:
             return bev
         bev_embed = bev.permute(0, 2, 1).reshape(bs, -1, self.bev_h, self.bev_w)
         # 'occ_cls' is the head kernel's fused argmax (int64, first-max tie rule like torch.argmax): `get_occ` returns it
         # instead of re-reading the 43 MB of logits (reference: softmax(-1).argmax(-1), bevformer_occ_head.py:211-212)
-        return {'bev_embed': bev_embed, 'occ': torch.stack(occs), 'flow': torch.stack(flows), 'occ_cls': torch.stack(clss)}
+        return {'bev_embed': bev_embed, 'occ': torch.stack(occs) if occs else None, 'flow': torch.stack(flows),
+                'occ_cls': torch.stack(clss)}
 
     def get_occ(self, preds_dicts, img_metas, rescale=False):
         cls = preds_dicts.get('occ_cls')

@@ -39,17 +39,19 @@ def make_cfg(**kw):
 
 
 # ------------------------------------------------------------------ a1  encoder.py:50-89
-def get_reference_points(H, W, Z=8, num_points_in_pillar=4, dim='3d', bs=1, dtype=torch.float32):
+def get_reference_points(H, W, Z=8, num_points_in_pillar=4, dim='3d', bs=1, dtype=torch.float32, device='cpu'):
+    """`device`: the reference builds these on the query's device (encoder.py:64); 'cuda' is used by bench.py's
+    gpu_eager_baseline leg only (the restated modules on stock torch kernels)."""
     if dim == '3d':
-        zs = torch.linspace(0.5, Z - 0.5, num_points_in_pillar, dtype=dtype).view(-1, 1, 1) \
+        zs = torch.linspace(0.5, Z - 0.5, num_points_in_pillar, dtype=dtype, device=device).view(-1, 1, 1) \
             .expand(num_points_in_pillar, H, W) / Z
-        xs = torch.linspace(0.5, W - 0.5, W, dtype=dtype).view(1, 1, W).expand(num_points_in_pillar, H, W) / W
-        ys = torch.linspace(0.5, H - 0.5, H, dtype=dtype).view(1, H, 1).expand(num_points_in_pillar, H, W) / H
+        xs = torch.linspace(0.5, W - 0.5, W, dtype=dtype, device=device).view(1, 1, W).expand(num_points_in_pillar, H, W) / W
+        ys = torch.linspace(0.5, H - 0.5, H, dtype=dtype, device=device).view(1, H, 1).expand(num_points_in_pillar, H, W) / H
         ref_3d = torch.stack((xs, ys, zs), -1)
         ref_3d = ref_3d.permute(0, 3, 1, 2).flatten(2).permute(0, 2, 1)
         return ref_3d[None].repeat(bs, 1, 1, 1)                      # (bs, D, H*W, 3)
-    ref_y, ref_x = torch.meshgrid(torch.linspace(0.5, H - 0.5, H, dtype=dtype),
-                                  torch.linspace(0.5, W - 0.5, W, dtype=dtype), indexing='ij')
+    ref_y, ref_x = torch.meshgrid(torch.linspace(0.5, H - 0.5, H, dtype=dtype, device=device),
+                                  torch.linspace(0.5, W - 0.5, W, dtype=dtype, device=device), indexing='ij')
     ref_y = ref_y.reshape(-1)[None] / H
     ref_x = ref_x.reshape(-1)[None] / W
     ref_2d = torch.stack((ref_x, ref_y), -1)
@@ -213,7 +215,8 @@ def bevformer_layer(p, prefix, cfg, query, key, value, bev_pos, ref_2d, bev_h, b
                     msda=msda_grid_sample, taps=None):
     # operation_order ('self_attn','norm','cross_attn','norm','ffn','norm')  (bevformer_base_occ.py:127-128)
     q = temporal_self_attention(p, prefix + '.attentions.0', cfg, query, prev_bev, bev_pos, ref_2d,
-                                torch.tensor([[bev_h, bev_w]]), torch.tensor([0]), msda=msda)
+                                torch.tensor([[bev_h, bev_w]], device=query.device), torch.tensor([0], device=query.device),
+                                msda=msda)
     if taps is not None:
         taps['tsa'] = q
     q = layer_norm(p, prefix + '.norms.0', q)
@@ -233,8 +236,8 @@ def bevformer_encoder(p, prefix, cfg, bev_query, key, value, bev_h, bev_w, bev_p
     pc = cfg['pc_range']
     bs = bev_query.size(1)
     ref_3d = get_reference_points(bev_h, bev_w, pc[5] - pc[2], cfg['num_points_in_pillar'], '3d', bs,
-                                  bev_query.dtype)
-    ref_2d = get_reference_points(bev_h, bev_w, dim='2d', bs=bs, dtype=bev_query.dtype)
+                                  bev_query.dtype, bev_query.device)
+    ref_2d = get_reference_points(bev_h, bev_w, dim='2d', bs=bs, dtype=bev_query.dtype, device=bev_query.device)
     reference_points_cam, bev_mask = point_sampling(ref_3d, pc, img_metas)
     shift_ref_2d = ref_2d.clone()
     bev_query = bev_query.permute(1, 0, 2)
@@ -273,7 +276,7 @@ def pack_camera_features(p, prefix, cfg, mlvl_feats):
         feat = feat + p[prefix + '.level_embeds'][None, None, lvl:lvl + 1, :]
         feat_flatten.append(feat)
     feat_flatten = torch.cat(feat_flatten, 2)
-    spatial_shapes = torch.as_tensor(spatial_shapes, dtype=torch.long)
+    spatial_shapes = torch.as_tensor(spatial_shapes, dtype=torch.long, device=feat_flatten.device)
     level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
     return feat_flatten.permute(0, 2, 1, 3), spatial_shapes, level_start_index  # (cam, Nv, B, C)
 

@@ -14,31 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_CFG = '/root/reference/projects/configs/bevformer/bevformer_base_occ.py'
 
 
-def head_cfg(cfg):
-    C = cfg['embed_dims']
-    return dict(
-        type='BEVFormerOccHead', pc_range=cfg['pc_range'], bev_h=cfg['bev_h'], bev_w=cfg['bev_w'],
-        num_classes=cfg['num_classes'], in_channels=C, sync_cls_avg_factor=True, with_box_refine=True, as_two_stage=False,
-        use_mask=False, loss_occ=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0),
-        loss_flow=dict(type='L1Loss', loss_weight=0.25),
-        transformer=dict(
-            type='TransformerOcc', pillar_h=cfg['pillar_h'], num_classes=cfg['num_classes'], norm_cfg=dict(type='BN'),
-            norm_cfg_3d=dict(type='BN3d'), use_3d=True, use_conv=False, rotate_prev_bev=True, use_shift=True,
-            use_can_bus=True, embed_dims=C, num_cams=cfg['num_cams'], rotate_center=cfg.get('rotate_center', [100, 100]),
-            encoder=dict(
-                type='BEVFormerEncoder', num_layers=cfg['num_layers'], pc_range=cfg['pc_range'],
-                num_points_in_pillar=cfg['num_points_in_pillar'], return_intermediate=False,
-                transformerlayers=dict(
-                    type='BEVFormerLayer',
-                    attn_cfgs=[dict(type='TemporalSelfAttention', embed_dims=C, num_levels=1),
-                               dict(type='SpatialCrossAttention', pc_range=cfg['pc_range'], num_cams=cfg['num_cams'],
-                                    deformable_attention=dict(type='MSDeformableAttention3D', embed_dims=C,
-                                                              num_points=cfg['sca_points'], num_levels=cfg['num_levels']),
-                                    embed_dims=C)],
-                    feedforward_channels=cfg['ffn_dim'], ffn_dropout=0.1,
-                    operation_order=('self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm')))),
-        positional_encoding=dict(type='LearnedPositionalEncoding', num_feats=C // 2, row_num_embed=cfg['bev_h'],
-                                 col_num_embed=cfg['bev_w']))
+head_cfg = fixtures.head_cfg          # registry config of the head for a fixture geometry (shared with bench.py)
 
 
 def test_plugin_state_dict_keys_equal_reference(golden_dir):

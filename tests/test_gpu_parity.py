@@ -169,6 +169,24 @@ def test_pack_levels_matches_get_bev_features(precision, use_cams):
         assert not torch.equal(got, with_cams[:, :, 0])
 
 
+def test_bf16_feature_input_equals_rounded_fp32_input():
+    """`occb200_engine_set_input_dtype(1)`: bf16 feature levels (on-device backbone / bf16 host pipeline) give bit-identical
+    results to fp32 levels holding the same bf16-rounded numbers; level sizes here hit the 16-byte and the scalar loads."""
+    cfg, params, feats, metas, _ = make_case('small6')
+    eng = engine_for(cfg, params, metas, 'bf16', tc=False)
+    f16 = [f[0].bfloat16().to(DEV).contiguous() for f in feats]
+    a = {k: v.clone() for k, v in eng.forward([f.float() for f in f16], want=('bev_embed', 'occ', 'flow')).items()}
+    eng.set_input_dtype(torch.bfloat16)
+    b = eng.forward(f16, want=('bev_embed', 'occ', 'flow'))
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    with pytest.raises(ValueError):                              # dtype contract is checked on the host
+        eng.forward([f.float() for f in f16])
+    host = [f.cpu().pin_memory() for f in f16]
+    occ_h, flow_h = eng.forward_host(host)
+    assert torch.equal(flow_h, b['flow'].cpu())
+
+
 # ------------------------------------------------------------------------------------------ full path, fp32 config
 def _check_fp32(cfg, params, feats, metas, prev, per_layer=True):
     O, _, _ = _oracle()
