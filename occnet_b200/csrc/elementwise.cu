@@ -277,3 +277,39 @@ int launch_bf16_to_f32(const bf16* src, float* dst, int64_t n, cudaStream_t stre
     return 0;
 }
 }  // namespace occ
+
+// ---- bf16 split of fp32 GEMM operands (fp32-grade tensor-core configuration): x = hi + lo + O(2^-17 |x|)
+namespace occ {
+namespace {
+// one thread = 8 consecutive elements of one source row; Ka, Kb multiples of 8
+__global__ void split_bf16_kernel(const float* __restrict__ a, int Ka, const float* __restrict__ b, int Kb, int64_t rows,
+                                  bf16* __restrict__ S)
+{
+    const int K = Ka + Kb, per_row = K >> 3;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * per_row) return;
+    const int64_t r = i / per_row;
+    const int c = (int)(i % per_row) * 8;
+    const float* src = c < Ka ? a + r * Ka + c : b + r * Kb + (c - Ka);
+    float v[8], hi[8], lo[8];
+    load8(src, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float h = __bfloat162float(__float2bfloat16_rn(v[k]));
+        hi[k] = h; lo[k] = v[k] - h;                           // exact in fp32 (Sterbenz-style: |lo| <= 2^-9 |x|)
+    }
+    bf16* row = S + r * (2 * (int64_t)K);
+    store8(row + c, hi);
+    store8(row + K + c, lo);
+}
+}  // namespace
+int launch_split_bf16(const float* a, int Ka, const float* b, int Kb, int64_t rows, bf16* S, cudaStream_t stream)
+{
+    OCC_CHECK(a && Ka % 8 == 0 && Kb % 8 == 0 && (Kb == 0 || b), "split_bf16: operands must be multiples of 8 wide");
+    const int64_t n = rows * ((Ka + Kb) >> 3);
+    if (n == 0) return 0;
+    split_bf16_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(a, Ka, b, Kb, rows, S);
+    OCC_CUDA(cudaGetLastError());
+    return 0;
+}
+}  // namespace occ

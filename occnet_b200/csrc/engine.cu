@@ -69,6 +69,10 @@ struct occb200_engine {
     DevBuf bev_queries, pos, pos_t32, cams_embeds, level_embeds;
     DevBuf pos_bf;                      // bev_pos as a bf16 row-major GEMM operand (folded TSA query projection)
     DevBuf qc_f32, qc_t, qc_pos_t;      // parameter-only layer-0 operands (query fp32 T32, bf16 query, bf16 query+pos), built once
+    // Self mode (prev_bev = None): layer 0's TemporalSelfAttention + its LayerNorm see only parameters (bev_queries, bev_pos,
+    // weights) -- the result is frame-independent and is computed ONCE at finalize by the same kernels (T32 fp32 + bf16 copy)
+    DevBuf l0_x_f32, l0_q_t;
+    bool l0_ready = false;
     DevBuf conv_w[2], conv_b[2], conv_wh[2];
     DevBuf sca_v_all_wh, sca_v_all_b, sca_value_all;     // value_proj of every layer, concatenated (tensor-core path)
     DevBuf hw1, hb1, hw2, hb2, fw1, fb1, fw2, fb2, head_w1h, head_w2h, head_b1c, head_b2c;
@@ -76,6 +80,8 @@ struct occb200_engine {
     DevBuf tokens, sca_value, q_f32, q_t, q_pos_t, q0_t, prev_t, tsa_value, tsa_value_prev, qproj, attn_out, x_f32,
         ffn_h, vox0, vox1, vox2, hits;
     DevBuf tap_layer, tap_tsa, tap_sca;
+    // fp32-grade tensor-core configuration (precision 0 + use_tensor_cores): bf16 [hi | lo] splits of the GEMM operands
+    DevBuf split_ws, tokens_split;
     // host-buffer variant
     DevBuf feats_dev[4], occ_i64_dev, flow_dev;
     // pipelined host-buffer variant: 2 slots, copies on their own streams, compute on the caller's stream
@@ -100,6 +106,22 @@ int upload(DevBuf& b, const float* src, size_t n)
 {
     if (b.alloc(n * sizeof(float))) return 2;
     OCC_CUDA(cudaMemcpy(b.p, src, n * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// [W_hi | W_hi | W_lo] (n x 3k bf16) of an n x k fp32 weight: B operand of gemm_tc_split3
+int upload_w3(DevBuf& b, const float* W, size_t n, size_t k)
+{
+    std::vector<__nv_bfloat16> h(n * 3 * k);
+    for (size_t r = 0; r < n; ++r)
+        for (size_t j = 0; j < k; ++j) {
+            const float w = W[r * k + j];
+            const __nv_bfloat16 hi = __float2bfloat16(w);
+            const __nv_bfloat16 lo = __float2bfloat16(w - __bfloat162float(hi));
+            h[r * 3 * k + j] = hi; h[r * 3 * k + k + j] = hi; h[r * 3 * k + 2 * k + j] = lo;
+        }
+    if (b.alloc(h.size() * 2)) return 2;
+    OCC_CUDA(cudaMemcpy(b.p, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -160,6 +182,23 @@ int gemm(occb200_engine* e, const TA* A, const TA* A2, int K1, const float* W, c
                                reinterpret_cast<const bf16*>(Wh), bias, residual, C, M, N, K, act, st);
         }
     }
+    if constexpr (sizeof(TA) == 4 && std::is_same<TC, float>::value) {
+        // fp32 storage + tensor cores: operand split into bf16 hi/lo, weights [W_hi | W_hi | W_lo], three passes in one
+        // tcgen05 GEMM (relative error ~2^-16: fp32-grade).  The camera tokens are split once per frame.
+        if (e->cfg.use_tensor_cores && e->cfg.precision == 0 && Wh != nullptr && e->split_ws.p != nullptr &&
+            gemm_tc_supported(M, N, 3 * K, 2 * K)) {
+            const bf16* S = e->split_ws.as<bf16>();
+            if ((const void*)A == e->tokens.p && A2 == nullptr && e->tokens_split.p != nullptr) {
+                S = e->tokens_split.as<bf16>();
+            } else {
+                const int Ka = A2 ? K1 : K;
+                if (launch_split_bf16(reinterpret_cast<const float*>(A), Ka, reinterpret_cast<const float*>(A2), K - Ka, M,
+                                      e->split_ws.as<bf16>(), st)) return 2;
+                e->launches++;
+            }
+            return gemm_tc_split3(S, K, reinterpret_cast<const bf16*>(Wh), bias, residual, C, M, N, act, st);
+        }
+    }
     if constexpr (std::is_same<TC, __half>::value) {
         OCC_CHECK(false, "gemm: fp16 outputs exist only on the tensor-core path");
     } else {
@@ -178,19 +217,29 @@ int gemm_ln_fused(occb200_engine* e, const bf16* A, const void* Wh, const float*
     return gemm_tc_ln(A, reinterpret_cast<const bf16*>(Wh), bias, residual, gamma, beta, pos, y_f32, y_t, y_pos_t, M, K, st);
 }
 
+enum { MODE_FRAME = 0, MODE_L0_TSA_ONLY = 1 };
+
 template <typename T>
 int forward_impl(occb200_engine* e, const float* const* feats, const float* prev_bev, float* bev_embed,
-                 float* occ_logits, float* flow, uint8_t* cls_u8, int64_t* cls_i64, cudaStream_t st)
+                 float* occ_logits, float* flow, uint8_t* cls_u8, int64_t* cls_i64, cudaStream_t st, int mode = MODE_FRAME)
 {
     const occb200_config& c = e->cfg;
     const int Nq = e->Nq, Nv = e->Nv, C = 256, ncam = c.num_cams;
     e->launches = 0;
     T* tokens = e->tokens.as<T>();
-    {
+    if (mode == MODE_FRAME) {
         ProfScope ps(e, st, CAT_PACK);
         if (launch_pack_levels<T>(reinterpret_cast<const void* const*>(feats), e->feats_bf16, e->lg, e->cams_embeds.as<float>(),
                                   e->level_embeds.as<float>(), ncam, C, Nv, tokens, st)) return 2;
         e->launches++;
+    }
+    if constexpr (sizeof(T) == 4) {
+        if (mode == MODE_FRAME && c.use_tensor_cores && e->tokens_split.p != nullptr) {
+            ProfScope ps(e, st, CAT_PACK);
+            if (launch_split_bf16(reinterpret_cast<const float*>(tokens), C, nullptr, 0, (int64_t)ncam * Nv,
+                                  e->tokens_split.as<bf16>(), st)) return 2;
+            e->launches++;
+        }
     }
     float* q_f32 = e->q_f32.as<float>();
     float* x_f32 = e->x_f32.as<float>();
@@ -203,7 +252,7 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
     // Layer-0 operands.  On the fused tensor-core path they were built once at finalize (parameters only); the
     // residual stream then rotates through {constant, q_f32, x_f32} without ever writing the constant buffer.
     const bool const_q = fuse_ln && e->qc_f32.p != nullptr;
-    const float* const qc_f32 = const_q ? e->qc_f32.as<float>() : nullptr;
+    const float* cbuf = const_q ? e->qc_f32.as<float>() : nullptr;     // the constant buffer in the rotation (never written)
     float* spare_f32 = nullptr;
     const T* q_in = q_t;                    // bf16/fp32 operand copy of the current query
     const T* q_pos_in = q_pos_t;            // ... of query + pos
@@ -219,7 +268,7 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
     auto advance = [&]() {                  // the LayerNorm output just written to x_f32 becomes the residual stream
         float* old = q_f32;
         q_f32 = x_f32;
-        x_f32 = (old == qc_f32) ? spare_f32 : old;
+        x_f32 = (old == cbuf) ? spare_f32 : old;
     };
     const bool has_prev = prev_bev != nullptr;
     const T* q0_t = nullptr;
@@ -247,7 +296,10 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
     void* qproj = e->qproj.p;
     T* attn_out = e->attn_out.as<T>();
     const bool hoist_v = sizeof(T) == 2 && c.use_tensor_cores && e->sca_value_all.p != nullptr;
-    if (hoist_v) {
+    // layer-0 TSA + LayerNorm folded into a constant (self mode only; OCC_NO_L0_FOLD=1 recomputes it every frame)
+    const bool l0_fold = mode == MODE_FRAME && const_q && !has_prev && e->l0_ready;
+    const T* q_t_in = q_t;                  // A operand of the SCA query projection (= the TSA LayerNorm output)
+    if (hoist_v && mode == MODE_FRAME) {
         e->launches++;
         ProfScope ps(e, st, CAT_GEMM);
         if (gemm_tc_blocked256((const bf16*)tokens, e->sca_v_all_wh.as<bf16>(), e->sca_v_all_b.as<float>(),
@@ -255,7 +307,17 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
     }
     for (int l = 0; l < c.num_layers; ++l) {
         LayerW& w = e->layers[l];
+        // self mode (prev_bev = None): W1 q + W2 (q + pos) = (W1 + W2) q + W2 pos -- the second operand is the CONSTANT
+        // bf16 pos, so no layer has to write (and the FFN LayerNorm epilogue has to read pos for) a bf16 copy of q + pos
+        const bool fold_pos = fuse_ln && !has_prev && w.tsa_q_wh_fold.p != nullptr && e->pos_bf.p != nullptr && q_half;
         // ---- temporal self-attention (temporal_self_attention.py:177-272)
+        if (l == 0 && l0_fold) {
+            // precomputed at finalize: residual stream := constant T32 buffer, SCA projection operand := constant bf16 copy
+            q_f32 = e->l0_x_f32.as<float>(); x_f32 = e->q_f32.as<float>(); spare_f32 = e->x_f32.as<float>();
+            cbuf = q_f32;
+            q_t_in = e->l0_q_t.as<T>();
+            q_in = q_t; q_pos_in = q_pos_t;
+        } else {
         T* v_cur = e->tsa_value.as<T>();
         T* v_prev = v_cur;
         if (gemm<T, T>(e, has_prev ? q0_t : q_in, nullptr, 0, w.tsa_v_w.as<float>(), w.tsa_v_wh.p,
@@ -265,9 +327,6 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
             if (gemm<T, T>(e, e->prev_t.as<T>(), nullptr, 0, w.tsa_v_w.as<float>(), w.tsa_v_wh.p,
                            w.tsa_v_b.as<float>(), nullptr, v_prev, Nq, C, C, ACT_NONE, st)) return 2;
         }
-        // self mode (prev_bev = None): W1 q + W2 (q + pos) = (W1 + W2) q + W2 pos -- the second operand is the CONSTANT
-        // bf16 pos, so no layer has to write (and the FFN LayerNorm epilogue has to read pos for) a bf16 copy of q + pos
-        const bool fold_pos = fuse_ln && !has_prev && w.tsa_q_wh_fold.p != nullptr && e->pos_bf.p != nullptr && q_half;
         if (fold_pos) {
             if (gemm<T, __half>(e, q_in, e->pos_bf.as<T>(), C, w.tsa_q_w.as<float>(), w.tsa_q_wh_fold.p, w.tsa_q_b.as<float>(),
                                 nullptr, (__half*)qproj, Nq, nq_tsa, 2 * C, ACT_NONE, st)) return 2;
@@ -285,8 +344,11 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
         }
         e->launches++;
         if (fuse_ln) {
+            float* y32 = mode == MODE_L0_TSA_ONLY ? e->l0_x_f32.as<float>() : x_f32;
+            bf16* y16 = mode == MODE_L0_TSA_ONLY ? e->l0_q_t.as<bf16>() : (bf16*)q_t;
             if (gemm_ln_fused(e, (const bf16*)attn_out, w.tsa_o_wh.p, w.tsa_o_b.as<float>(), q_f32, w.ln_g[0].as<float>(),
-                              w.ln_b[0].as<float>(), nullptr, x_f32, (bf16*)q_t, nullptr, Nq, C, st)) return 2;
+                              w.ln_b[0].as<float>(), nullptr, y32, y16, nullptr, Nq, C, st)) return 2;
+            if (mode == MODE_L0_TSA_ONLY) return 0;
             advance();
             q_in = q_t; q_pos_in = q_pos_t;
         } else {
@@ -302,13 +364,15 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
             }
             e->launches++;
         }
+        }   // (layer-0 TSA fold)
         // ---- spatial cross-attention (spatial_cross_attention.py:128-175, :334-393)
         {
-            const int rc = q_half ? gemm<T, __half>(e, q_t, nullptr, 0, w.sca_q_w.as<float>(), w.sca_q_wh.p, w.sca_q_b.as<float>(),
+            const int rc = q_half ? gemm<T, __half>(e, q_t_in, nullptr, 0, w.sca_q_w.as<float>(), w.sca_q_wh.p, w.sca_q_b.as<float>(),
                                                     nullptr, (__half*)qproj, Nq, nq_sca, C, ACT_NONE, st)
-                                  : gemm<T, float>(e, q_t, nullptr, 0, w.sca_q_w.as<float>(), w.sca_q_wh.p, w.sca_q_b.as<float>(),
+                                  : gemm<T, float>(e, q_t_in, nullptr, 0, w.sca_q_w.as<float>(), w.sca_q_wh.p, w.sca_q_b.as<float>(),
                                                    nullptr, (float*)qproj, Nq, nq_sca, C, ACT_NONE, st);
             if (rc) return 2;
+            q_t_in = q_t;
         }
         const T* sca_val = e->sca_value.as<T>();
         if (hoist_v) {
@@ -489,7 +553,7 @@ void occb200_engine_destroy(occb200_engine* e)
                          &w.tsa_q_wh_fold};
         for (DevBuf* b : all) b->release();
     }
-    DevBuf* all[] = {&e->pos_bf, &e->qc_f32, &e->qc_t, &e->qc_pos_t, &e->bev_queries, &e->pos, &e->pos_t32, &e->cams_embeds, &e->level_embeds, &e->conv_w[0], &e->conv_w[1],
+    DevBuf* all[] = {&e->split_ws, &e->tokens_split, &e->l0_x_f32, &e->l0_q_t, &e->pos_bf, &e->qc_f32, &e->qc_t, &e->qc_pos_t, &e->bev_queries, &e->pos, &e->pos_t32, &e->cams_embeds, &e->level_embeds, &e->conv_w[0], &e->conv_w[1],
                      &e->conv_b[0], &e->conv_b[1], &e->conv_wh[0], &e->conv_wh[1], &e->sca_v_all_wh, &e->sca_v_all_b, &e->sca_value_all, &e->hw1, &e->hb1, &e->hw2, &e->hb2,
                      &e->fw1, &e->fb1, &e->fw2, &e->fb2, &e->head_w1h, &e->head_w2h, &e->head_b1c, &e->head_b2c, &e->tokens, &e->sca_value, &e->q_f32, &e->q_t,
                      &e->q_pos_t, &e->q0_t, &e->prev_t, &e->tsa_value, &e->tsa_value_prev, &e->qproj, &e->attn_out,
@@ -525,6 +589,7 @@ int occb200_engine_load_param(occb200_engine* e, const char* key, const float* d
     if (!ok) { set_last_error("unknown parameter key: " + k); return 3; }
     e->host_params[k].assign(data, data + numel);
     e->finalized = false;
+    e->l0_ready = false;
     return 0;
 }
 
@@ -534,6 +599,7 @@ int occb200_engine_finalize(occb200_engine* e)
     const occb200_config& c = e->cfg;
     const int C = 256, Nq = e->Nq, F = c.ffn_dim, od = c.out_dim, mid = C / c.pillar_h;
     const bool tc = c.precision == 1 && c.use_tensor_cores;
+    const bool tc32 = c.precision == 0 && c.use_tensor_cores;      // fp32 storage, split-bf16 tensor-core GEMMs
     {
         GETP(bq, "bev_embedding.weight", (size_t)Nq * C);
         if (upload(e->bev_queries, bq->data(), bq->size())) return 2;
@@ -575,6 +641,7 @@ int occb200_engine_finalize(occb200_engine* e)
             if (!W || !B) return 3;
             if (upload(wbuf, W->data(), W->size()) || upload(bbuf, B->data(), B->size())) return 2;
             if (tc && wh && upload_bf16(*wh, W->data(), W->size())) return 2;
+            if (tc32 && wh && upload_w3(*wh, W->data(), n, k)) return 2;
             return 0;
         };
         auto up_cat = [&](DevBuf& wbuf, DevBuf& bbuf, DevBuf* wh, const std::string& n1, const std::string& n2,
@@ -589,6 +656,7 @@ int occb200_engine_finalize(occb200_engine* e)
             B.insert(B.end(), B2->begin(), B2->end());
             if (upload(wbuf, W.data(), W.size()) || upload(bbuf, B.data(), B.size())) return 2;
             if (tc && wh && upload_bf16(*wh, W.data(), W.size())) return 2;
+            if (tc32 && wh && upload_w3(*wh, W.data(), r1 + r2, k)) return 2;
             if (tc && fold) {                                    // k = 2C: fold the first half of every row into (W1 + W2)
                 std::vector<float> Wf(W);
                 const size_t half = k / 2;
@@ -702,7 +770,26 @@ int occb200_engine_finalize(occb200_engine* e)
         e->vox2.alloc(nvox * od * es) || e->hits.alloc(Nq)) return 2;
     OCC_CUDA(cudaMemset(e->q_f32.p, 0, nq_pad * C * 4));
     OCC_CUDA(cudaMemset(e->x_f32.p, 0, nq_pad * C * 4));
+    if (tc32) {
+        const size_t kmax = (size_t)std::max(2 * C, F);
+        if (e->split_ws.alloc((size_t)Nq * 2 * kmax * 2) || e->tokens_split.alloc(ntok * 2 * C * 2)) return 2;
+    }
     e->host_params.clear();
+    e->l0_ready = false;
+    if (tc && e->qc_f32.p != nullptr && getenv("OCC_NO_L0_FOLD") == nullptr) {
+        // Layer 0's TemporalSelfAttention (value_proj, query projection over [bev_queries | pos], gather, output_proj) and
+        // its LayerNorm depend on parameters only when prev_bev is None: run the frame path's own kernels once, here.
+        const size_t rows_pad = ((size_t)Nq + 127) / 128 * 128;
+        if (e->l0_x_f32.alloc(rows_pad * C * 4) || e->l0_q_t.alloc((size_t)Nq * C * 2)) return 2;
+        OCC_CUDA(cudaMemset(e->l0_x_f32.p, 0, rows_pad * C * 4));
+        const bool taps = e->taps;
+        e->taps = false;
+        const int rc = forward_impl<bf16>(e, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, MODE_L0_TSA_ONLY);
+        e->taps = taps;
+        if (rc) return rc;
+        OCC_CUDA(cudaDeviceSynchronize());
+        e->l0_ready = true;
+    }
     e->finalized = true;
     return 0;
 }

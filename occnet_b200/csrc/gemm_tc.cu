@@ -498,6 +498,8 @@ Plan make_plan(int N, int K, bool ln, int stg_bytes = 4096)
             if (N % bn != 0 || bn > N) continue;
             if ((long)bn * K * 2 <= 131072) { p.BN = bn; break; }
         }
+        if (K > 512 && p.BN != 0 && p.BN < 128) p.BN = 0;     // split-operand GEMMs (K' = 3K): a 64-wide resident block would
+                                                              // re-read A once per 64 columns; stream W with a wide tile instead
         if (p.BN == 0) {                                      // no resident candidate: largest tile that divides N
             for (int bn : cands) if (N % bn == 0 && bn <= N) { p.BN = bn; break; }
         }
@@ -515,20 +517,23 @@ Plan make_plan(int N, int K, bool ln, int stg_bytes = 4096)
 }
 
 struct MapKey {
-    const void* p; uint64_t d0, d1; uint32_t b0, b1;
-    bool operator<(const MapKey& o) const { return std::tie(p, d0, d1, b0, b1) < std::tie(o.p, o.d0, o.d1, o.b0, o.b1); }
+    const void* p; uint64_t d0, d1, ld; uint32_t b0, b1;
+    bool operator<(const MapKey& o) const { return std::tie(p, d0, d1, ld, b0, b1) < std::tie(o.p, o.d0, o.d1, o.ld, o.b0, o.b1); }
 };
 
-int cached_map_2d(const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows, CUtensorMap* out)
+// row-major bf16 [rows, inner] with a row pitch of `ld` elements (0 = dense)
+int cached_map_2d(const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows, CUtensorMap* out,
+                  uint64_t ld = 0)
 {
     static std::map<MapKey, CUtensorMap> cache;
     static std::mutex mu;
     std::lock_guard<std::mutex> g(mu);
-    const MapKey k{base, inner, rows, box_inner, box_rows};
+    if (ld == 0) ld = inner;
+    const MapKey k{base, inner, rows, ld, box_inner, box_rows};
     auto it = cache.find(k);
     if (it == cache.end()) {
         CUtensorMap m;
-        const uint64_t dims[2] = {inner, rows}, strides[1] = {inner * 2};
+        const uint64_t dims[2] = {inner, rows}, strides[1] = {ld * 2};
         const uint32_t box[2] = {box_inner, box_rows};
         if (make_tensor_map_bf16(&m, base, 2, dims, strides, box, 128)) return 1;
         if (cache.size() > 4096) cache.clear();
@@ -560,7 +565,7 @@ int cached_map_out(const void* base, uint64_t cols, uint64_t rows, uint64_t bloc
 
 template <typename TC, bool LN>
 int launch(const bf16* A, const bf16* A2, int K1, const bf16* W, const float* bias, const float* residual, TC* C,
-           LnArgs ln, int M, int N, int K, int act, cudaStream_t stream, bool blocked_out = false)
+           LnArgs ln, int M, int N, int K, int act, cudaStream_t stream, bool blocked_out = false, int lda = 0, int lda2 = 0)
 {
     if (A2 == nullptr) K1 = K;
     // 16-bit outputs without a residual leave through TMA stores of [32 rows x 32 columns] (OCC_GEMM_NO_TMA_STORE=1:
@@ -571,8 +576,8 @@ int launch(const bf16* A, const bf16* A2, int K1, const bf16* W, const float* bi
     const Plan p = make_plan(N, K, LN, stg_bytes);
     OCC_CHECK(p.BN > 0 && p.stages >= 2 && K % 64 == 0 && K1 % 64 == 0 && M > 0, "gemm_tc: unsupported shape");
     CUtensorMap tmA, tmA2, tmW;
-    if (cached_map_2d(A, (uint64_t)K1, (uint64_t)M, BLOCK_K, BLOCK_M, &tmA)) return 1;
-    if (A2) { if (cached_map_2d(A2, (uint64_t)(K - K1), (uint64_t)M, BLOCK_K, BLOCK_M, &tmA2)) return 1; }
+    if (cached_map_2d(A, (uint64_t)K1, (uint64_t)M, BLOCK_K, BLOCK_M, &tmA, (uint64_t)lda)) return 1;
+    if (A2) { if (cached_map_2d(A2, (uint64_t)(K - K1), (uint64_t)M, BLOCK_K, BLOCK_M, &tmA2, (uint64_t)lda2)) return 1; }
     else tmA2 = tmA;
     if (cached_map_2d(W, (uint64_t)K, (uint64_t)N, BLOCK_K, (uint32_t)p.BN, &tmW)) return 1;
     CUtensorMap tmC = tmW;
@@ -646,6 +651,15 @@ int gemm_tc(const bf16* A, const bf16* A2, int K1, const bf16* W, const float* b
             int M, int N, int K, int act, cudaStream_t stream)
 {
     return launch<TC, false>(A, A2, K1, W, bias, residual, C, LnArgs{}, M, N, K, act, stream);
+}
+
+// fp32-grade GEMM on the tensor cores: S = [hi | lo] (bf16 split of an fp32 operand, row pitch 2*Ks), W3 = [W_hi | W_hi | W_lo]
+// (N x 3*Ks).  C = hi.W_hi + lo.W_hi + hi.W_lo  (the lo.lo term, 2^-16 relative, is dropped) as ONE GEMM with K' = 3*Ks whose
+// A operand is the concatenation [S (2*Ks columns) | first Ks columns of S again] -- two tensor maps over the same buffer.
+int gemm_tc_split3(const bf16* S, int Ks, const bf16* W3, const float* bias, const float* residual, float* C, int M, int N,
+                   int act, cudaStream_t stream)
+{
+    return launch<float, false>(S, S, 2 * Ks, W3, bias, residual, C, LnArgs{}, M, N, 3 * Ks, act, stream, false, 2 * Ks, 2 * Ks);
 }
 
 int gemm_tc_blocked256(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, int N, int K, cudaStream_t stream)

@@ -21,6 +21,13 @@ int gemm_tc_ln(const bf16* A, const bf16* W, const float* bias, const float* res
 // Used to project the camera tokens with the value_proj weights of ALL encoder layers in one pass over the tokens.
 int gemm_tc_blocked256(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, int N, int K, cudaStream_t stream);
 
+// fp32-grade product of an fp32 operand (given as its bf16 split S = [hi | lo], [M, 2*Ks]) with fp32 weights (given as
+// W3 = [W_hi | W_hi | W_lo], [N, 3*Ks] bf16): 3 tensor-core passes in one launch, relative error ~2^-16.
+int gemm_tc_split3(const bf16* S, int Ks, const bf16* W3, const float* bias, const float* residual, float* C, int M, int N,
+                   int act, cudaStream_t stream);
+// S[r] = [hi(a[r]) hi(b[r]) | lo(a[r]) lo(b[r])], hi = bf16(x), lo = bf16(x - hi); b may be null (Kb = 0)
+int launch_split_bf16(const float* a, int Ka, const float* b, int Kb, int64_t rows, bf16* S, cudaStream_t stream);
+
 int launch_bf16_to_f32(const bf16* src, float* dst, int64_t n, cudaStream_t stream);
 
 }  // namespace occ

@@ -188,12 +188,12 @@ def test_bf16_feature_input_equals_rounded_fp32_input():
 
 
 # ------------------------------------------------------------------------------------------ full path, fp32 config
-def _check_fp32(cfg, params, feats, metas, prev, per_layer=True):
+def _check_fp32(cfg, params, feats, metas, prev, per_layer=True, tc=False):
     O, _, _ = _oracle()
     taps = {}
     with torch.no_grad():
         want = O.head_forward(params, cfg, feats, metas, prev_bev=None if prev is None else prev.clone(), taps=taps)
-    eng = engine_for(cfg, params, metas, 'fp32')
+    eng = engine_for(cfg, params, metas, 'fp32', tc=tc)
     eng.enable_taps(True)
     pb = None
     if prev is not None:
@@ -233,6 +233,16 @@ def test_engine_fp32_small6_two_layers():
 
 def test_engine_fp32_temporal_prev_bev():
     _check_fp32(*make_case('small6', with_prev=True, ang=3.0, rotate_center=[20, 20]))
+
+
+@pytest.mark.parametrize('prev', [False, True])
+def test_engine_fp32_tensor_core_split_gemm(prev):
+    """fp32 storage + tcgen05: every nn.Linear as ONE 3-pass bf16-split GEMM (hi.hi + lo.hi + hi.lo, ~2^-16 relative): the
+    reference-precision configuration on the tensor cores, same 1e-3 bar per layer tap and output as the CUDA-core one."""
+    code = ("import sys; sys.path.insert(0, 'tests'); import test_gpu_parity as t; "
+            f"t._check_fp32(*t.make_case('small6', with_prev={prev}, ang={3.0 if prev else None}, rotate_center=[20, 20]), tc=True); "
+            "print('OK')")
+    assert 'OK' in _run_isolated(code)
 
 
 @pytest.mark.parametrize('name', ['toy', 'small6', 'small6_prev'])
@@ -552,14 +562,24 @@ def _ray_counters_vs_scene(pred_cls, pred_flow):
     return rm.counters.cpu().numpy()
 
 
-def test_full_size_six_layers_fp32_vs_oracle_golden(golden_dir):
-    """BASELINE configs[1]: 6 x 928x1600 -> 200x200 BEV, SIX encoder layers, voxel decoder, heads, fp32 configuration.
+@pytest.mark.parametrize('tc', [False, True])
+def test_full_size_six_layers_fp32_vs_oracle_golden(tc, golden_dir):
+    if tc:                                                       # tcgen05 path in a child process (a fault must not poison this one)
+        code = ("import sys; sys.path.insert(0, 'tests'); import test_gpu_parity as t; "
+                f"t._full6_fp32(True, {golden_dir!r}); print('OK')")
+        assert 'OK' in _run_isolated(code, timeout=600)
+    else:
+        _full6_fp32(False, golden_dir)
+
+
+def _full6_fp32(tc, golden_dir):
+    """tc=True: the split-bf16 tcgen05 GEMMs (fp32-grade), tc=False: CUDA-core GEMMs.  BASELINE configs[1]: 6 x 928x1600 -> 200x200 BEV, SIX encoder layers, voxel decoder, heads, fp32 configuration.
     Every per-layer tap and every output within 1e-3 of the oracle (golden: tests/golden/gen_fullsize.py, oracle pinned
     bit-exactly to the reference modules); class volume and Ray-mIoU counters as the reference's metric sees them."""
     from sampling import N_OUT, N_TAP
     cfg, params, feats, metas, _ = _full6_case()
     g = np.load(os.path.join(golden_dir, 'full6_fp32.npz'))
-    eng = engine_for(cfg, params, metas, 'fp32')
+    eng = engine_for(cfg, params, metas, 'fp32', tc=tc)
     eng.enable_taps(True)
     out = eng.forward([f[0].to(DEV) for f in feats], want=('bev_embed', 'occ', 'flow', 'occ_cls'))
     torch.cuda.synchronize()
@@ -586,7 +606,7 @@ def test_full_size_six_layers_fp32_vs_oracle_golden(golden_dir):
     rel = np.abs(cnt[:5 * n] - g['counters'][:5 * n]).sum() / max(g['counters'][:5 * n].sum(), 1)
     rep['counter_rel_diff_vs_oracle_counters'] = rel
     assert rel < 2e-3, rel
-    _report('full6_fp32', rep)
+    _report('full6_fp32' + ('_tc_split' if tc else '_cuda_cores'), rep)
 
 
 def _check_full6_bf16(prev, golden_dir):
@@ -640,6 +660,31 @@ def test_full_size_six_layers_bf16_temporal_prev_bev(golden_dir):
     """Same with a previous BEV (BASELINE configs[2]: TemporalSelfAttention over [prev_bev, current]): the has_prev branch
     of the fused path (unfolded query projection over prev_t / q+pos, q+pos written by the FFN LayerNorm epilogue)."""
     _check_full6_bf16(True, golden_dir)
+
+
+def test_layer0_tsa_constant_fold_is_bit_identical():
+    """Self mode (prev_bev None): layer 0's TemporalSelfAttention + LayerNorm depend on parameters only and are computed once
+    at finalize by the frame path's own kernels; an engine built with OCC_NO_L0_FOLD=1 recomputes them every frame.
+    Same kernels, same inputs -> bit-identical outputs; with a prev_bev the fold must not be used."""
+    code = r"""
+import os, sys, torch
+sys.path.insert(0, 'tests')
+import test_gpu_parity as t
+cfg, params, feats, metas, prev = t.make_case('small6', with_prev=True)
+fd = [f[0].to(t.DEV) for f in feats]
+a = t.engine_for(cfg, params, metas, 'bf16', tc=True)
+os.environ['OCC_NO_L0_FOLD'] = '1'
+b = t.engine_for(cfg, params, metas, 'bf16', tc=True)
+del os.environ['OCC_NO_L0_FOLD']
+for pb in (None, prev):
+    oa = a.forward(fd, prev_bev=pb); la = a.launches_per_frame
+    ob = b.forward(fd, prev_bev=pb); lb = b.launches_per_frame
+    for k in oa:
+        assert torch.equal(oa[k], ob[k]), k
+    assert (lb - la) == (4 if pb is None else 0), (la, lb)
+print('OK')
+"""
+    assert 'OK' in _run_isolated(code)
 
 
 # ------------------------------------------------------------------------------------------ drop-in module API
