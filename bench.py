@@ -316,8 +316,9 @@ def run_ours(args):
         dist.all_gather_object(numa_all, numa)
 
     # ---- extra single-GPU legs (rank 0, N = 1 only): drop-in module call, fp32 configuration, stock-kernel comparator
-    dropin = fp32_leg = eager = None
+    dropin = fp32_leg = eager = temporal = None
     if world == 1:
+        temporal = run_temporal_leg(args, cfg, eng, frames_dev)
         dropin = run_dropin_leg(args, cfg, params, metas, frames_host, dev) if not args.no_dropin else None
         fp32_leg = run_fp32_leg(args, cfg, params, metas, frames_f32, dev) if args.precision != 'fp32' else None
         eager = run_gpu_eager_baseline(cfg, params, metas, frames_f32, dev) if not args.no_eager else None
@@ -420,6 +421,7 @@ def run_ours(args):
         'kernel_ms_per_frame': {k: round(v[0] / prof_frames, 4) for k, v in prof.items()},
         'parity': parity,
         'fp32_config': fp32_leg,
+        'temporal_config': temporal,
         'gpu_eager_baseline': eager,
         'cpu_baseline': cpu,
         **({'backbone_experimental': backbone} if backbone is not None else {}),
@@ -456,6 +458,35 @@ def run_dropin_leg(args, cfg, params, metas, frames_host, dev):
                 'api': 'BEVFormerOcc.forward(return_loss=False, img_feats=<pinned host feats .to(cuda)>, img_metas) -> CPU '
                        'LongTensor / FloatTensor (synchronous, one frame per call)'}
     except Exception as e:                                            # noqa: BLE001 -- a leg, not the headline
+        return {'error': f'{type(e).__name__}: {e}'[:300]}
+
+
+def run_temporal_leg(args, cfg, eng, frames_dev):
+    """BASELINE configs[2] (+ TemporalSelfAttention over history): video mode -- every frame's TSA attends to the previous
+    frame's BEV, rotated by can_bus[-1] (3 degrees here; index map applied inside the engine).  4 history frames are run
+    first (the reference's queue_length), then a stream of frames is timed; each produces occupancy AND the next prev_bev."""
+    try:
+        from occnet_b200.engine import rotation_index_map
+        eng.set_prev_rotation(rotation_index_map(cfg['bev_h'], cfg['bev_w'], 3.0, cfg.get('rotate_center', [100, 100])))
+        want = ('bev_embed', 'flow', 'occ_cls')
+        prev = None
+        for i in range(4):                                           # history (obtain_history_bev recurrence)
+            prev = eng.forward(frames_dev[i % len(frames_dev)], prev_bev=prev, want=('bev_embed',))['bev_embed']
+        torch.cuda.synchronize()
+        n = 2 * args.frames_per_step
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            prev = eng.forward(frames_dev[i % len(frames_dev)], prev_bev=prev, want=want)['bev_embed']
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        lpf = eng.launches_per_frame
+        eng.set_prev_rotation(None)
+        return {'value': round(1e3 / ms, 2), 'unit': 'samples/s', 'ms_per_frame': round(ms, 4), 'frames': n,
+                'launches_per_frame': lpf, 'history_frames': 4, 'tsa_queue': 2,
+                'what': 'device-resident, prev_bev = previous frame BEV (rotated in-engine), same precision as the headline'}
+    except Exception as e:                                            # noqa: BLE001
         return {'error': f'{type(e).__name__}: {e}'[:300]}
 
 

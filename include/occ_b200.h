@@ -96,6 +96,13 @@ int occb200_engine_finalize(occb200_engine* e);
  * img_metas[0]['img_shape'][0][:2] (encoder.py:133-134). */
 int occb200_engine_set_cameras(occb200_engine* e, const float* cam_mat, const float* zs, int img_h, int img_w);
 
+/* Rotation of the NEXT frames' prev_bev (TransformerOcc.get_bev_features, transformer_occ.py:189-205: torchvision
+ * rotate(prev_bev as (C,H,W), can_bus[-1] degrees, center=rotate_center), nearest, zero fill).  A nearest-neighbour
+ * rotation is a row permutation of the (Nq, C) BEV: map_host[q] (HOST int32 [Nq]) = source BEV cell of output cell q,
+ * -1 = outside (zeros).  The engine applies it while casting prev_bev to the GEMM operand type -- prev_bev is then
+ * passed UN-rotated to occb200_engine_forward.  NULL clears it (prev_bev is taken as already rotated).  Synchronous. */
+int occb200_engine_set_prev_rotation(occb200_engine* e, const int32_t* map_host);
+
 /* Element type of the feature levels handed to _forward / _forward_host / _submit_host from now on: 0 = fp32 (default,
  * the reference's dtype), 1 = bf16 (same [num_cams, C, h, w] layout, pointers passed through the same arguments): what
  * an on-device backbone emits, and half the PCIe bytes for host pipelines that already hold bf16 features. */

@@ -313,3 +313,35 @@ int launch_split_bf16(const float* a, int Ka, const float* b, int Kb, int64_t ro
     return 0;
 }
 }  // namespace occ
+
+// ---- prev_bev rotation as a row gather (transformer_occ.py:195-205: torchvision `rotate`, nearest, zero fill): the host
+//      hands over the index map source_row[q] (-1 = outside), this kernel applies it while producing the GEMM operand copy
+namespace occ {
+namespace {
+template <typename T>
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ map, int rows, int C,
+                                   T* __restrict__ dst, float* __restrict__ dst_f32)
+{
+    const int per_row = C >> 3;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)rows * per_row) return;
+    const int r = (int)(i / per_row), c = (int)(i % per_row) * 8;
+    const int sr = map ? map[r] : r;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (sr >= 0) load8(src + (int64_t)sr * C + c, v);
+    if (dst) store8(dst + (int64_t)r * C + c, v);
+    if (dst_f32) store8(dst_f32 + (int64_t)r * C + c, v);
+}
+}  // namespace
+template <typename T>
+int launch_gather_rows(const float* src, const int32_t* map, int rows, int C, T* dst, float* dst_f32, cudaStream_t stream)
+{
+    OCC_CHECK(C % 8 == 0, "gather_rows: C must be a multiple of 8");
+    const int64_t n = (int64_t)rows * (C >> 3);
+    gather_rows_kernel<T><<<ceil_div(n, 256), 256, 0, stream>>>(src, map, rows, C, dst, dst_f32);
+    OCC_CUDA(cudaGetLastError());
+    return 0;
+}
+template int launch_gather_rows<float>(const float*, const int32_t*, int, int, float*, float*, cudaStream_t);
+template int launch_gather_rows<bf16>(const float*, const int32_t*, int, int, bf16*, float*, cudaStream_t);
+}  // namespace occ

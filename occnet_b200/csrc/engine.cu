@@ -63,6 +63,8 @@ struct occb200_engine {
     LevelGeom lg;
     ScaParams sp;
     bool cameras_set = false, finalized = false, taps = false;
+    DevBuf rot_map;                     // occb200_engine_set_prev_rotation: source row of every BEV cell (int32, -1 = outside)
+    bool rot_set = false;
     int feats_bf16 = 0;                 // occb200_engine_set_input_dtype: feature levels arrive as bf16 instead of fp32
     std::map<std::string, std::vector<float>> host_params;
     std::vector<LayerW> layers;
@@ -275,7 +277,10 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
     if (has_prev) {
         // encoder.py:204-209: value = stack([prev_bev, bev_query]) built ONCE before the layer loop, so
         // queue 1 keeps seeing the layer-0 query in every layer.
-        if (launch_cast<T>(prev_bev, e->prev_t.as<T>(), (int64_t)Nq * C, st)) return 2;
+        // (transformer_occ.py:195-205) the rotation of prev_bev about rotate_center is a nearest-neighbour row permutation:
+        // applied here, fused with the operand cast, from the index map set by occb200_engine_set_prev_rotation
+        if (launch_gather_rows<T>(prev_bev, e->rot_set ? e->rot_map.as<int32_t>() : nullptr, Nq, C, e->prev_t.as<T>(), nullptr, st))
+            return 2;
         e->launches++;
         if (const_q) {
             q0_t = e->qc_t.as<T>();
@@ -553,7 +558,7 @@ void occb200_engine_destroy(occb200_engine* e)
                          &w.tsa_q_wh_fold};
         for (DevBuf* b : all) b->release();
     }
-    DevBuf* all[] = {&e->split_ws, &e->tokens_split, &e->l0_x_f32, &e->l0_q_t, &e->pos_bf, &e->qc_f32, &e->qc_t, &e->qc_pos_t, &e->bev_queries, &e->pos, &e->pos_t32, &e->cams_embeds, &e->level_embeds, &e->conv_w[0], &e->conv_w[1],
+    DevBuf* all[] = {&e->rot_map, &e->split_ws, &e->tokens_split, &e->l0_x_f32, &e->l0_q_t, &e->pos_bf, &e->qc_f32, &e->qc_t, &e->qc_pos_t, &e->bev_queries, &e->pos, &e->pos_t32, &e->cams_embeds, &e->level_embeds, &e->conv_w[0], &e->conv_w[1],
                      &e->conv_b[0], &e->conv_b[1], &e->conv_wh[0], &e->conv_wh[1], &e->sca_v_all_wh, &e->sca_v_all_b, &e->sca_value_all, &e->hw1, &e->hb1, &e->hw2, &e->hb2,
                      &e->fw1, &e->fb1, &e->fw2, &e->fb2, &e->head_w1h, &e->head_w2h, &e->head_b1c, &e->head_b2c, &e->tokens, &e->sca_value, &e->q_f32, &e->q_t,
                      &e->q_pos_t, &e->q0_t, &e->prev_t, &e->tsa_value, &e->tsa_value_prev, &e->qproj, &e->attn_out,
@@ -916,6 +921,17 @@ int occb200_engine_wait_host(occb200_engine* e, int slot)
     if (!s.busy) return 0;
     OCC_CUDA(cudaEventSynchronize(s.d2h_done));
     s.busy = false;
+    return 0;
+}
+
+int occb200_engine_set_prev_rotation(occb200_engine* e, const int32_t* map_host)
+{
+    OCC_CHECK(e, "null engine");
+    if (map_host == nullptr) { e->rot_set = false; return 0; }
+    for (int q = 0; q < e->Nq; ++q) OCC_CHECK(map_host[q] >= -1 && map_host[q] < e->Nq, "rotation map entry out of range");
+    if (e->rot_map.bytes != (size_t)e->Nq * 4 && e->rot_map.alloc((size_t)e->Nq * 4)) return 2;
+    OCC_CUDA(cudaMemcpy(e->rot_map.p, map_host, (size_t)e->Nq * 4, cudaMemcpyHostToDevice));
+    e->rot_set = true;
     return 0;
 }
 

@@ -48,6 +48,24 @@ def camera_params(cfg, img_metas):
     return cam, zs, int(h), int(w)
 
 
+_ROT_CACHE = {}
+
+
+def rotation_index_map(bev_h, bev_w, angle_deg, center):
+    """Index map of the reference's prev_bev rotation (transformer_occ.py:195-205), obtained from the SAME torchvision
+    call applied to an image of cell indices -- so ties, centre handling and out-of-image cells are torchvision's, not a
+    re-derivation: returns (bev_h*bev_w,) int32, entry q = source cell of output cell q, -1 = outside (zero fill)."""
+    key = (bev_h, bev_w, float(angle_deg), tuple(center))
+    if key not in _ROT_CACHE:
+        from torchvision.transforms.functional import rotate
+        idx = torch.arange(1, bev_h * bev_w + 1, dtype=torch.float32).reshape(1, bev_h, bev_w)   # exact in fp32 (< 2^24)
+        rot = rotate(idx, float(angle_deg), center=list(center))                                 # nearest, fill 0
+        if len(_ROT_CACHE) > 64:
+            _ROT_CACHE.clear()
+        _ROT_CACHE[key] = (rot.reshape(-1).to(torch.int64) - 1).to(torch.int32).numpy()
+    return _ROT_CACHE[key]
+
+
 class OccEngine:
     def __init__(self, cfg, params, precision='fp32', use_tensor_cores=False, device='cuda:0'):
         if not torch.cuda.is_available():
@@ -86,6 +104,16 @@ class OccEngine:
     def set_cameras(self, img_metas):
         cam, zs, h, w = camera_params(self.cfg, img_metas)
         _lib.check(self.lib.occb200_engine_set_cameras(self._h, _lib.ptr(cam), _lib.ptr(zs), h, w))
+
+    def set_prev_rotation(self, index_map):
+        """`index_map` (Nq,) int32 numpy / tensor: source BEV cell of every output cell (-1 = outside), e.g. from
+        `rotation_index_map`; None = prev_bev arrives already rotated."""
+        if index_map is None:
+            _lib.check(self.lib.occb200_engine_set_prev_rotation(self._h, None))
+            return
+        m = np.ascontiguousarray(index_map.cpu().numpy() if isinstance(index_map, torch.Tensor) else index_map, np.int32)
+        assert m.shape == (self.Nq,)
+        _lib.check(self.lib.occb200_engine_set_prev_rotation(self._h, _lib.ptr(m)))
 
     def _check_feats(self, feats, cuda):
         """A mismatched tensor would be an out-of-bounds device read in the pack kernel: fail on the host instead."""

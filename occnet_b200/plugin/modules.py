@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ..engine import OccEngine
+from ..engine import OccEngine, rotation_index_map
 from ..mmcv_shim import (ATTENTION, BACKBONES, DETECTORS, HEADS, NECKS, TRANSFORMER, TRANSFORMER_LAYER, TRANSFORMER_LAYER_SEQUENCE,
                          BaseModule, ConfigDict, ConvModule, ModuleList, TransformerLayerSequence, build_attention,
                          build_feedforward_network, build_head, build_loss, build_norm_layer,
@@ -440,13 +440,13 @@ class TransformerOcc(BaseModule):
         nn.init.normal_(self.cams_embeds)
 
     def rotate_prev(self, prev_bev, bev_h, bev_w, img_metas):
-        """reference :189-205: prev_bev (bs, Nq, C) rotated by can_bus[-1] degrees about `rotate_center` (nearest)."""
-        from torchvision.transforms.functional import rotate
-        out = prev_bev.clone()
+        """reference :189-205: prev_bev (bs, Nq, C) rotated by can_bus[-1] degrees about `rotate_center` (nearest, zero
+        fill), as a row gather with torchvision's own index map (`occnet_b200.engine.rotation_index_map`)."""
+        out = torch.zeros_like(prev_bev)
         for i in range(prev_bev.shape[0]):
-            t = prev_bev[i].reshape(bev_h, bev_w, -1).permute(2, 0, 1)
-            t = rotate(t, img_metas[i]['can_bus'][-1], center=self.rotate_center)
-            out[i] = t.permute(1, 2, 0).reshape(bev_h * bev_w, -1)
+            m = torch.from_numpy(rotation_index_map(bev_h, bev_w, img_metas[i]['can_bus'][-1], self.rotate_center)).to(prev_bev.device)
+            ok = m >= 0
+            out[i, ok] = prev_bev[i, m[ok].long()]
         return out
 
 
@@ -495,16 +495,23 @@ class BEVFormerOccHead(BaseModule):
         _need_cuda(mlvl_feats[0], 'BEVFormerOccHead')
         bs = mlvl_feats[0].shape[0]
         eng = self._get_engine(mlvl_feats[0].device, [tuple(f.shape[-2:]) for f in mlvl_feats])
+        rot_maps = None
         if prev_bev is not None:
-            if prev_bev.shape[1] != self.bev_h * self.bev_w:
+            if prev_bev.dim() == 4:                                            # (B, C, H, W) = a previous 'bev_embed' (:193-194)
+                prev_bev = prev_bev.reshape(bs, -1, self.bev_h * self.bev_w).permute(0, 2, 1)
+            elif prev_bev.shape[1] != self.bev_h * self.bev_w:
                 prev_bev = prev_bev.permute(1, 0, 2)
             if self.transformer.rotate_prev_bev:
-                prev_bev = self.transformer.rotate_prev(prev_bev, self.bev_h, self.bev_w, img_metas)
+                # nearest-neighbour rotation = a row permutation: torchvision computes the index map (160 KB, cached per
+                # angle), the engine applies it while casting prev_bev to its operand type (no 41 MB torch round trip)
+                rot_maps = [rotation_index_map(self.bev_h, self.bev_w, img_metas[b]['can_bus'][-1], self.transformer.rotate_center)
+                            for b in range(bs)]
         bevs, occs, flows, clss = [], [], [], []
         want = ('bev_embed', 'occ', 'flow', 'occ_cls_i64') if (self.test_logits or not test) else ('bev_embed', 'flow', 'occ_cls_i64')
         for b in range(bs):
             eng.set_cameras([img_metas[b] if b == 0 else dict(img_metas[b], ego2lidar=img_metas[0]['ego2lidar'],
                                                               img_shape=img_metas[0]['img_shape'])])
+            eng.set_prev_rotation(None if rot_maps is None else rot_maps[b])
             fb = [f[b] for f in mlvl_feats]
             if fb[0].dtype != eng.feat_dtype:                                 # fp32 (reference dtype) or bf16 features
                 if fb[0].dtype == torch.bfloat16 or eng.feat_dtype == torch.bfloat16:
@@ -603,7 +610,7 @@ class BEVFormerOcc(BaseModule):
 
     def __init__(self, pts_bbox_head=None, img_backbone=None, img_neck=None, use_grid_mask=False, video_test_mode=False,
                  train_cfg=None, test_cfg=None, pretrained=None, feature_extractor=None, native_backbone=False,
-                 backbone_precision='bf16', **kwargs):
+                 backbone_precision='bf16', temporal_test=False, **kwargs):
         super().__init__()
         if pts_bbox_head is not None:
             pts_bbox_head = dict(pts_bbox_head)
@@ -618,6 +625,11 @@ class BEVFormerOcc(BaseModule):
         self.native_backbone, self.backbone_precision = native_backbone, backbone_precision
         self._backbone_engine, self._backbone_key = None, None
         self.video_test_mode = video_test_mode
+        # temporal_test=False reproduces the reference exactly: its forward_test always passes prev_bev=None
+        # (bevformer_occ.py:243-244), `prev_frame_info` is dead state there.  temporal_test=True (with video_test_mode)
+        # turns the cache on the way upstream BEVFormer uses it: the previous frame's BEV (kept on the device) feeds the
+        # next frame of the SAME scene; a new `scene_token` (or prev_bev_exists=False) resets it.
+        self.temporal_test = temporal_test
         self.prev_frame_info = {'prev_bev': None, 'scene_token': None, 'prev_pos': 0, 'prev_angle': 0}
 
     def extract_img_feat(self, img, img_metas=None, len_queue=None):
@@ -671,7 +683,17 @@ class BEVFormerOcc(BaseModule):
         metas = img_metas[0] if isinstance(img_metas[0], (list, tuple)) else img_metas
         if isinstance(img, (list, tuple)):
             img = img[0]
-        _, occ, flow = self.simple_test(metas, img, img_feats=img_feats, prev_bev=None, **kwargs)   # reference: prev_bev=None
+        prev_bev = None                                                                             # reference: prev_bev=None
+        if self.temporal_test and self.video_test_mode:
+            info = self.prev_frame_info
+            tok = metas[0].get('scene_token')
+            if tok != info['scene_token'] or not metas[0].get('prev_bev_exists', True):
+                info['prev_bev'] = None                                                             # first frame of a scene
+            info['scene_token'] = tok
+            prev_bev = info['prev_bev']
+        new_prev_bev, occ, flow = self.simple_test(metas, img, img_feats=img_feats, prev_bev=prev_bev, **kwargs)
+        if self.temporal_test and self.video_test_mode:
+            self.prev_frame_info['prev_bev'] = new_prev_bev                                         # (B, C, H, W), stays on the device
         return {'occ_results': occ.cpu(), 'flow_results': flow.cpu()}
 
     def forward(self, return_loss=False, **kwargs):

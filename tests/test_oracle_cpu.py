@@ -474,3 +474,21 @@ def test_full_size_goldens_are_committed_and_consistent(golden_dir):
     assert 0.6 < free < 0.9                                          # FREE_BIAS keeps the metric rays travelling
     b = np.load(os.path.join(golden_dir, 'full6_bf16.npz'))
     assert (b['occ_cls'] == g['occ_cls']).mean() > 0.99 and np.abs(b['occ_sub'] - g['occ_sub']).max() < 6e-2
+
+
+@pytest.mark.parametrize('hw,center', [((40, 40), [20, 20]), ((200, 200), [100, 100]), ((30, 50), [25, 15])])
+def test_rotation_index_map_is_torchvisions_rotation(hw, center):
+    """The engine rotates prev_bev by gathering rows through `rotation_index_map` (host side, torchvision applied to an
+    image of cell indices).  Applying that map must equal the reference's rotation of the feature map itself
+    (transformer_occ.py:195-205) bit for bit, including zero fill and ties."""
+    from occnet_b200.engine import rotation_index_map
+    h, w = hw
+    prev = torch.randn(h * w, 16, generator=torch.Generator().manual_seed(0))
+    for ang in (0.0, 3.0, -17.5, 90.0, 181.3, 45.0):
+        want = O.rotate_prev_bev(prev.clone(), h, w, ang, center)
+        m = torch.from_numpy(rotation_index_map(h, w, ang, center)).long()
+        got = torch.zeros_like(prev)
+        got[m >= 0] = prev[m[m >= 0]]
+        assert torch.equal(got, want), ang
+        if ang == 0.0:
+            assert torch.equal(m, torch.arange(h * w))
