@@ -63,6 +63,7 @@ struct occb200_engine {
     LevelGeom lg;
     ScaParams sp;
     bool cameras_set = false, finalized = false, taps = false;
+    bool value_head_major = false;      // SCA value maps as [layer][head][token][32] (pair-fetch gather) instead of [layer][token][256]
     DevBuf rot_map;                     // occb200_engine_set_prev_rotation: source row of every BEV cell (int32, -1 = outside)
     bool rot_set = false;
     int feats_bf16 = 0;                 // occb200_engine_set_input_dtype: feature levels arrive as bf16 instead of fp32
@@ -308,7 +309,7 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
         e->launches++;
         ProfScope ps(e, st, CAT_GEMM);
         if (gemm_tc_blocked256((const bf16*)tokens, e->sca_v_all_wh.as<bf16>(), e->sca_v_all_b.as<float>(),
-                               e->sca_value_all.as<bf16>(), ncam * Nv, c.num_layers * C, C, st)) return 2;
+                               e->sca_value_all.as<bf16>(), ncam * Nv, c.num_layers * C, C, st, e->value_head_major)) return 2;
     }
     for (int l = 0; l < c.num_layers; ++l) {
         LayerW& w = e->layers[l];
@@ -386,7 +387,10 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
                               e->sca_value.as<T>(), ncam * Nv, C, C, ACT_NONE, st)) return 2;
         {
             ProfScope ps(e, st, CAT_SCA);
-            if (launch_sca_fused<T>(sca_val, qproj, q_half, e->sp, e->lg, Nv, attn_out, e->hits.as<uint8_t>(), st)) return 2;
+            if (hoist_v && e->value_head_major) {
+                if (launch_sca_pair(reinterpret_cast<const bf16*>(sca_val), qproj, q_half, e->sp, e->lg, Nv,
+                                    reinterpret_cast<bf16*>(attn_out), e->hits.as<uint8_t>(), st)) return 2;
+            } else if (launch_sca_fused<T>(sca_val, qproj, q_half, e->sp, e->lg, Nv, attn_out, e->hits.as<uint8_t>(), st)) return 2;
         }
         e->launches++;
         if (fuse_ln) {
@@ -703,7 +707,9 @@ int occb200_engine_finalize(occb200_engine* e)
             B.insert(B.end(), b->begin(), b->end());
         }
         if (upload_bf16(e->sca_v_all_wh, W.data(), W.size()) || upload(e->sca_v_all_b, B.data(), B.size())) return 2;
-        if (e->sca_value_all.alloc((size_t)c.num_layers * c.num_cams * e->Nv * C * 2)) return 2;
+        if (e->sca_value_all.alloc((size_t)c.num_layers * c.num_cams * e->Nv * C * 2 + 256)) return 2;   // (+ one pair over-read)
+        OCC_CUDA(cudaMemset(e->sca_value_all.p, 0, e->sca_value_all.bytes));
+        e->value_head_major = getenv("OCC_VALUE_ROWMAJOR") == nullptr;
     }
     // decoder: fold BatchNorm3d (eval) into the conv weights; torch layout [Cout][Cin][kz][ky][kx] -> [tap][Cin][Cout]
     for (int i = 0; i < 2; ++i) {

@@ -87,7 +87,8 @@ template <typename TC, bool LN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)          // 10 warps -> 3 on one SMSP -> <= 168 regs (16K per SMSP)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmC,
-               int c_tma /* 0: none, 1: [M,N] row-major, 2: n-blocks as separate [M,BN] matrices */, int stg_bytes,
+               int c_tma /* 0: none, 1: [M,N] row-major, 2: n-blocks as separate [M,BN] matrices,
+                            3: head-major value maps [n-block][column/32][M][32] (one 64-byte row per (head, token)) */, int stg_bytes,
                const float* __restrict__ bias,
                const float* __restrict__ residual, TC* __restrict__ C, LnArgs ln, int M, int N, int BN, int nk,
                int nk1, int act, int w_resident, int stages, long long ldc, long long nblk_stride,
@@ -418,8 +419,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tc::fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        if (c_tma == 2) tc::tma_store_3d(&tmC, stg, c0, row0, n_blk);
-                        else            tc::tma_store_3d(&tmC, stg, col, row0, 0);
+                        if (c_tma == 3)      tc::tma_store_4d(&tmC, stg, 0, row0, c0 >> 5, n_blk);
+                        else if (c_tma == 2) tc::tma_store_3d(&tmC, stg, c0, row0, n_blk);
+                        else                 tc::tma_store_3d(&tmC, stg, col, row0, 0);
                         tc::tma_store_commit();
                     }
                 }
@@ -563,9 +565,30 @@ int cached_map_out(const void* base, uint64_t cols, uint64_t rows, uint64_t bloc
     return 0;
 }
 
+// head-major output map for c_tma == 3: dims {32 channels, rows, heads = BN/32, n-blocks}, box {32, 32, 1, 1}
+int cached_map_out_heads(const void* base, uint64_t rows, uint64_t heads, uint64_t blocks, CUtensorMap* out)
+{
+    static std::map<std::tuple<const void*, uint64_t, uint64_t, uint64_t>, CUtensorMap> cache;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> g(mu);
+    const auto k = std::make_tuple(base, rows, heads, blocks);
+    auto it = cache.find(k);
+    if (it == cache.end()) {
+        CUtensorMap m;
+        const uint64_t dims[4] = {32, rows, heads, blocks}, strides[3] = {64, rows * 64, heads * rows * 64};
+        const uint32_t box[4] = {32, 32, 1, 1};
+        if (make_tensor_map_bf16(&m, base, 4, dims, strides, box, 64)) return 1;
+        if (cache.size() > 4096) cache.clear();
+        it = cache.emplace(k, m).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
 template <typename TC, bool LN>
 int launch(const bf16* A, const bf16* A2, int K1, const bf16* W, const float* bias, const float* residual, TC* C,
-           LnArgs ln, int M, int N, int K, int act, cudaStream_t stream, bool blocked_out = false, int lda = 0, int lda2 = 0)
+           LnArgs ln, int M, int N, int K, int act, cudaStream_t stream, bool blocked_out = false, int lda = 0, int lda2 = 0,
+           bool head_major = false)
 {
     if (A2 == nullptr) K1 = K;
     // 16-bit outputs without a residual leave through TMA stores of [32 rows x 32 columns] (OCC_GEMM_NO_TMA_STORE=1:
@@ -584,7 +607,10 @@ int launch(const bf16* A, const bf16* A2, int K1, const bf16* W, const float* bi
     int c_tma = 0;
     if (use_tma_store) {
         const uint32_t box_cols = 32u;
-        if (blocked_out) {
+        if (head_major) {
+            if (cached_map_out_heads(C, (uint64_t)M, (uint64_t)(p.BN / 32), (uint64_t)(N / p.BN), &tmC)) return 1;
+            c_tma = 3;
+        } else if (blocked_out) {
             if (cached_map_out(C, (uint64_t)p.BN, (uint64_t)M, (uint64_t)(N / p.BN), box_cols, &tmC)) return 1;
             c_tma = 2;
         } else {
@@ -662,11 +688,14 @@ int gemm_tc_split3(const bf16* S, int Ks, const bf16* W3, const float* bias, con
     return launch<float, false>(S, S, 2 * Ks, W3, bias, residual, C, LnArgs{}, M, N, 3 * Ks, act, stream, false, 2 * Ks, 2 * Ks);
 }
 
-int gemm_tc_blocked256(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, int N, int K, cudaStream_t stream)
+int gemm_tc_blocked256(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, int N, int K, cudaStream_t stream,
+                       bool head_major)
 {
     const Plan p = make_plan(N, K, false);
     OCC_CHECK(p.BN == 256 && N % 256 == 0, "gemm_tc_blocked256: N must be a multiple of 256 with 256-wide tiles");
-    return launch<bf16, false>(A, nullptr, 0, W, bias, nullptr, C, LnArgs{}, M, N, K, ACT_NONE, stream, true);
+    static const bool no_tma_store = getenv("OCC_GEMM_NO_TMA_STORE") != nullptr;
+    OCC_CHECK(!(head_major && no_tma_store), "head-major value maps need the TMA-store epilogue");
+    return launch<bf16, false>(A, nullptr, 0, W, bias, nullptr, C, LnArgs{}, M, N, K, ACT_NONE, stream, true, 0, 0, head_major);
 }
 
 // residual, y_f32 and pos are in the T32 block layout (elementwise.cu), rows padded to a multiple of 32

@@ -19,7 +19,10 @@ int gemm_tc_ln(const bf16* A, const bf16* W, const float* bias, const float* res
 
 // C = A.W^T + bias with N = n*256: output written as n separate contiguous [M,256] bf16 matrices (C + i*M*256).
 // Used to project the camera tokens with the value_proj weights of ALL encoder layers in one pass over the tokens.
-int gemm_tc_blocked256(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, int N, int K, cudaStream_t stream);
+// head_major: every [M,256] block is instead written as 8 head planes [head][M][32] (one 64-byte row per (head, token)):
+// the layout the pair-fetch gather kernel reads (both x-neighbours of a head's bilinear sample are adjacent in memory).
+int gemm_tc_blocked256(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, int N, int K, cudaStream_t stream,
+                       bool head_major = false);
 
 // fp32-grade product of an fp32 operand (given as its bf16 split S = [hi | lo], [M, 2*Ks]) with fp32 weights (given as
 // W3 = [W_hi | W_hi | W_lo], [N, 3*Ks] bf16): 3 tensor-core passes in one launch, relative error ~2^-16.

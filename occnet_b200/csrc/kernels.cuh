@@ -27,6 +27,9 @@ int launch_tsa_fused(const T* value_prev, const T* value_cur, const void* qproj,
 template <typename T>
 int launch_sca_fused(const T* value, const void* qproj, bool qproj_is_half, const ScaParams& sp, const LevelGeom& lg, int Nv,
                      T* out, uint8_t* hits, cudaStream_t stream);
+// same gather on head-major value maps [8 heads][num_cams*Nv tokens][32] (pair-fetch kernel, bf16 production path)
+int launch_sca_pair(const bf16* value_hm, const void* qproj, bool qproj_is_half, const ScaParams& sp, const LevelGeom& lg,
+                    int Nv, bf16* out, uint8_t* hits, cudaStream_t stream);
 int launch_project_pillars(const ScaParams& sp, float* ref_cam, uint8_t* mask, cudaStream_t stream);
 
 // ---- backbone_kernels.cu (image backbone + neck, channels-last; first version, see the file header)

@@ -371,6 +371,136 @@ sca_pipe_kernel(const bf16* __restrict__ value, const QT* __restrict__ qproj, Sc
 }
 
 // ------------------------------------------------------------------------------------------
+// Pair-fetch variant of the production gather (head-major value maps, written by the value_proj GEMM's TMA-store epilogue):
+//   value_hm [8 heads][T = num_cams * Nv tokens][32] bf16 -- one 64-byte row per (head, token), so the two x-neighbours of a
+//   bilinear sample are ADJACENT: 8 lanes fetch the 128 contiguous bytes {left pixel | right pixel} of one (head, row) with
+//   one 128-bit load each, and a warp instruction covers 4 heads x 128 B.  A sample costs 2 such instructions per head group
+//   (upper row, lower row) instead of 4 corner instructions of 8 x 64 B: the same bytes in half as many 128-byte lines when
+//   the pair is line-aligned (even token), three quarters on average -- the row-major layout touched one line per (head,
+//   corner), and the kernel is bound by L1 lines per request (profiles/README.md).
+//   Lane map in phase 2: hl = lane / 8 (head within the group of 4), j = lane % 8: side = j / 4 (left / right pixel),
+//   slice = j % 4 (8 channels).  Two head groups -> 2 x 8 accumulators per lane; left and right partial sums are combined
+//   with one shuffle per accumulator at the end.  Phase 1 (descriptors) is the row-major kernel's.
+template <int NS, int DEPTH, typename Geom>
+__device__ __forceinline__ void gather_descs_pair(float (&acc)[8], const uint4* dsm, int side, Geom geom)
+{
+    uint4 d[DEPTH + 1];
+    uint4 v[DEPTH + 1][2];
+#pragma unroll
+    for (int i = 0; i < NS + DEPTH; ++i) {
+        if (i < NS) {
+            const int slot = i % (DEPTH + 1);
+            d[slot] = dsm[i * 8];
+            const bf16* base; int W;
+            geom(i, base, W);
+            if (d[slot].x & CODE_VALID) {
+                const bf16* p = base + (int64_t)(d[slot].x & CODE_OFF_MASK) * 32;
+                v[slot][0] = __ldg(reinterpret_cast<const uint4*>(p));
+                v[slot][1] = __ldg(reinterpret_cast<const uint4*>(p + (int64_t)W * 32));
+            }
+        }
+        if (i >= DEPTH) {
+            const int slot = (i - DEPTH) % (DEPTH + 1);
+            if (d[slot].x & CODE_VALID) {
+                const uint32_t w0 = side ? (d[slot].y >> 16) : d[slot].y;     // upper row: right / left corner weight
+                const uint32_t w1 = side ? (d[slot].z >> 16) : d[slot].z;     // lower row
+                fma_word4(acc, v[slot][0], w0); fma_word4(acc, v[slot][1], w1);
+            }
+        }
+    }
+}
+
+template <typename QT, int DEPTH, int MINB, int NW>
+__global__ void __launch_bounds__(NW * 32, MINB)
+sca_pair_kernel(const bf16* __restrict__ value_hm, const QT* __restrict__ qproj, ScaParams sp, LevelGeom lg, int Nv,
+                long long T, bf16* __restrict__ out, uint8_t* __restrict__ hits)
+{
+    __shared__ uint4 descs[NW][32 * 8];                          // [warp][sample = point*4 + level][head]
+    const int Nq = sp.bev_h * sp.bev_w;
+    const int q = blockIdx.x * NW + (threadIdx.x >> 5);
+    if (q >= Nq) return;
+    const int lane = threadIdx.x & 31, head = lane >> 2, s = lane & 3;   // phase-1 roles: (head, owned level)
+    const int hl = lane >> 3, j = lane & 7, side = j >> 2;               // phase-2 roles
+    const unsigned FULL = 0xffffffffu;
+
+    const float xs = __fdiv_rn((float)(q % sp.bev_w) + 0.5f, (float)sp.bev_w);
+    const float ys = __fdiv_rn((float)(q / sp.bev_w) + 0.5f, (float)sp.bev_h);
+    float ru[2], rv[2];
+    unsigned vis = 0;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int c = r * 4 + (lane >> 3), z = lane & 7;
+        bool ok = false;
+        ru[r] = 0.f; rv[r] = 0.f;
+        if (c < sp.num_cams && z < sp.D) project_point(sp.cam_mat[c], xs, ys, sp.zs[z], sp, ru[r], rv[r], ok);
+        const unsigned b = __ballot_sync(FULL, ok);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if ((b >> (8 * k)) & 0xffu) vis |= 1u << (r * 4 + k);
+    }
+    const int count = __popc(vis);
+    if (hits && lane == 0) hits[q] = (uint8_t)count;
+
+    float acc0[8], acc1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc0[i] = 0.f; acc1[i] = 0.f; }
+    uint4* dw = descs[threadIdx.x >> 5];
+    const int own_W = s == 0 ? lg.w[0] : s == 1 ? lg.w[1] : s == 2 ? lg.w[2] : lg.w[3];
+    const int own_H = s == 0 ? lg.h[0] : s == 1 ? lg.h[1] : s == 2 ? lg.h[2] : lg.h[3];
+    const int own_start = s == 0 ? lg.start[0] : s == 1 ? lg.start[1] : s == 2 ? lg.start[2] : lg.start[3];
+    const float own_w = (float)own_W, own_h = (float)own_H;
+
+    for (int c = 0; c < sp.num_cams; ++c) {
+        if (!((vis >> c) & 1u)) continue;                                // warp-uniform
+        {
+            const QT* qp = qproj + (int64_t)q * 768;
+            float off[16], wl[8];
+            load_q<16>(qp + head * 64 + s * 16, off);
+            load_q<8>(qp + 512 + head * 32 + s * 8, wl);
+            float mx = wl[0];
+#pragma unroll
+            for (int i = 1; i < 8; ++i) mx = fmaxf(mx, wl[i]);
+            mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 2));
+            float sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { wl[i] = __expf(wl[i] - mx); sum += wl[i]; }
+            sum += __shfl_xor_sync(FULL, sum, 1);
+            sum += __shfl_xor_sync(FULL, sum, 2);
+            const float inv = __fdividef(1.f, sum);
+            const int r = c >> 2;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                const int asrc = (c & 3) * 8 + (p % sp.D);               // Z-anchor interleave (:366-373)
+                const float u = __shfl_sync(FULL, r ? ru[1] : ru[0], asrc);
+                const float v = __shfl_sync(FULL, r ? rv[1] : rv[0], asrc);
+                const float w_im = fmaf(u, own_w, off[2 * p] - 0.5f);
+                const float h_im = fmaf(v, own_h, off[2 * p + 1] - 0.5f);
+                dw[(p * 4 + s) * 8 + head] = make_desc(prep_sample(h_im, w_im, wl[p] * inv, own_H, own_W, own_start));
+            }
+        }
+        __syncwarp();
+        // value_hm + (head * T + cam * Nv) * 32 + j * 8: lanes j = 0..7 of a head read 128 contiguous bytes
+        const bf16* v0 = value_hm + ((int64_t)hl * T + (int64_t)c * Nv) * 32 + j * 8;
+        const bf16* v1 = v0 + 4 * T * 32;
+        gather_descs_pair<32, DEPTH>(acc0, dw + hl, side, [&](int i, const bf16*& base, int& W) { base = v0; W = lg.w[i & 3]; });
+        gather_descs_pair<32, DEPTH>(acc1, dw + 4 + hl, side, [&](int i, const bf16*& base, int& W) { base = v1; W = lg.w[i & 3]; });
+        __syncwarp();
+    }
+    const float scale = (float)max(count, 1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        acc0[i] += __shfl_xor_sync(FULL, acc0[i], 4);                    // left-pixel lanes + right-pixel lanes
+        acc1[i] += __shfl_xor_sync(FULL, acc1[i], 4);
+    }
+    if (side == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { acc0[i] = __fdiv_rn(acc0[i], scale); acc1[i] = __fdiv_rn(acc1[i], scale); }
+        store8(out + (int64_t)q * 256 + hl * 32 + j * 8, acc0);
+        store8(out + (int64_t)q * 256 + (4 + hl) * 32 + j * 8, acc1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Operator boundary: value [B,Nv,M,C] f32, loc [B,Nq,M,L,P,2] (x,y), w [B,Nq,M,L,P] -> [B,Nq,M*C]
 // One thread per (b, q, head, 8-channel slice) when C % 8 == 0, otherwise per channel.
 template <int VEC>
@@ -680,6 +810,27 @@ template int launch_sca_fused<float>(const float*, const void*, bool, const ScaP
                                      uint8_t*, cudaStream_t);
 template int launch_sca_fused<bf16>(const bf16*, const void*, bool, const ScaParams&, const LevelGeom&, int, bf16*,
                                     uint8_t*, cudaStream_t);
+
+int launch_sca_pair(const bf16* value_hm, const void* qproj_v, bool q_half, const ScaParams& sp, const LevelGeom& lg, int Nv,
+                    bf16* out, uint8_t* hits, cudaStream_t stream)
+{
+    OCC_CHECK(lg.num_levels == 4 && sp.num_cams <= 8 && sp.D <= 8 && sp.D >= 1 && 8 % sp.D == 0,
+              "sca_pair: supports 4 levels, <= 8 cameras, pillar anchors in {1,2,4,8}");
+    for (int l = 0; l < 4; ++l) OCC_CHECK(lg.h[l] >= 2 && lg.w[l] >= 2, "sca_pair: every level must be at least 2x2");
+    const int Nq = sp.bev_h * sp.bev_w;
+    const long long T = (long long)sp.num_cams * Nv;
+    // 6 CTAs/SM caps the kernel at 80 registers (a few spills outside the gather loop); OCC_SCA_PAIR_MINB=5 trades occupancy
+    // for none (measured variants: profiles/README.md)
+    static const int minb = getenv("OCC_SCA_PAIR_MINB") ? atoi(getenv("OCC_SCA_PAIR_MINB")) : 6;
+    if (q_half) {
+        if (minb == 5) sca_pair_kernel<__half, 1, 5, 4><<<ceil_div(Nq, 4), 128, 0, stream>>>(value_hm, (const __half*)qproj_v, sp, lg, Nv, T, out, hits);
+        else           sca_pair_kernel<__half, 1, 6, 4><<<ceil_div(Nq, 4), 128, 0, stream>>>(value_hm, (const __half*)qproj_v, sp, lg, Nv, T, out, hits);
+    } else {
+        sca_pair_kernel<float, 1, 6, 4><<<ceil_div(Nq, 4), 128, 0, stream>>>(value_hm, (const float*)qproj_v, sp, lg, Nv, T, out, hits);
+    }
+    OCC_CUDA(cudaGetLastError());
+    return 0;
+}
 
 int launch_project_pillars(const ScaParams& sp, float* ref_cam, uint8_t* mask, cudaStream_t stream)
 {
