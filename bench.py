@@ -119,7 +119,7 @@ def algorithmic_work(cfg, s, tc=True, feat_bytes=4):
     # compulsory bytes = operands read + results written (weights are KB-sized and stay in SMEM / L2)
     ntok = nc * Nv
     per_layer = (Nq * C * s + Nq * C * s                              # TSA value_proj
-                 + Nq * 2 * C * s + Nq * 192 * qb                      # TSA offsets+weights (A = [q | pos] or [q | q+pos])
+                 + (Nq * C * s + Nq * 192 * 4 if qb == 2 else Nq * 2 * C * s) + Nq * 192 * qb   # TSA offsets+weights (folded: q + fp32 const)
                  + 2 * (Nq * C * s + Nq * C * 4 + Nq * C * 4 + Nq * C * s)   # out_proj + LN (TSA, SCA): A, residual, y fp32, y bf16
                  + Nq * C * s + Nq * 768 * qb                          # SCA offsets+weights
                  + Nq * C * s + Nq * F * s                             # FFN1

@@ -49,7 +49,9 @@ struct LayerW {
     DevBuf ln_g[3], ln_b[3];
     // bf16 copies for the tensor-core path
     DevBuf tsa_v_wh, tsa_q_wh, tsa_o_wh, sca_q_wh, sca_v_wh, sca_o_wh, ffn1_wh, ffn2_wh;
-    DevBuf tsa_q_wh_fold;   // [W1 + W2 | W2]: W1 q + W2 (q + pos) == (W1 + W2) q + W2 pos  (self mode, prev_bev = None)
+    // self mode (prev_bev = None): W1 q + W2 (q + pos) + b == (W1 + W2) q + [W2 pos + b]; the bracket depends on parameters
+    // only -> an fp32 [Nq,192] constant per layer, added by the GEMM epilogue (K = 256, weight block resident, A read once)
+    DevBuf tsa_q_wh_fold, tsa_q_const;
 };
 
 }  // namespace
@@ -315,7 +317,7 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
         LayerW& w = e->layers[l];
         // self mode (prev_bev = None): W1 q + W2 (q + pos) = (W1 + W2) q + W2 pos -- the second operand is the CONSTANT
         // bf16 pos, so no layer has to write (and the FFN LayerNorm epilogue has to read pos for) a bf16 copy of q + pos
-        const bool fold_pos = fuse_ln && !has_prev && w.tsa_q_wh_fold.p != nullptr && e->pos_bf.p != nullptr && q_half;
+        const bool fold_pos = fuse_ln && !has_prev && w.tsa_q_wh_fold.p != nullptr && w.tsa_q_const.p != nullptr && q_half;
         // ---- temporal self-attention (temporal_self_attention.py:177-272)
         if (l == 0 && l0_fold) {
             // precomputed at finalize: residual stream := constant T32 buffer, SCA projection operand := constant bf16 copy
@@ -334,8 +336,8 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
                            w.tsa_v_b.as<float>(), nullptr, v_prev, Nq, C, C, ACT_NONE, st)) return 2;
         }
         if (fold_pos) {
-            if (gemm<T, __half>(e, q_in, e->pos_bf.as<T>(), C, w.tsa_q_w.as<float>(), w.tsa_q_wh_fold.p, w.tsa_q_b.as<float>(),
-                                nullptr, (__half*)qproj, Nq, nq_tsa, 2 * C, ACT_NONE, st)) return 2;
+            if (gemm<T, __half>(e, q_in, nullptr, 0, w.tsa_q_w.as<float>(), w.tsa_q_wh_fold.p, nullptr,
+                                w.tsa_q_const.as<float>(), (__half*)qproj, Nq, nq_tsa, C, ACT_NONE, st)) return 2;
         } else {
             const T* qa = has_prev ? e->prev_t.as<T>() : q_in;
             const int rc = q_half ? gemm<T, __half>(e, qa, q_pos_in, C, w.tsa_q_w.as<float>(), w.tsa_q_wh.p, w.tsa_q_b.as<float>(),
@@ -559,7 +561,7 @@ void occb200_engine_destroy(occb200_engine* e)
                          &w.sca_v_w, &w.sca_v_b, &w.sca_o_w, &w.sca_o_b, &w.ffn1_w, &w.ffn1_b, &w.ffn2_w, &w.ffn2_b,
                          &w.ln_g[0], &w.ln_g[1], &w.ln_g[2], &w.ln_b[0], &w.ln_b[1], &w.ln_b[2], &w.tsa_v_wh,
                          &w.tsa_q_wh, &w.tsa_o_wh, &w.sca_q_wh, &w.sca_v_wh, &w.sca_o_wh, &w.ffn1_wh, &w.ffn2_wh,
-                         &w.tsa_q_wh_fold};
+                         &w.tsa_q_wh_fold, &w.tsa_q_const};
         for (DevBuf* b : all) b->release();
     }
     DevBuf* all[] = {&e->rot_map, &e->split_ws, &e->tokens_split, &e->l0_x_f32, &e->l0_q_t, &e->pos_bf, &e->qc_f32, &e->qc_t, &e->qc_pos_t, &e->bev_queries, &e->pos, &e->pos_t32, &e->cams_embeds, &e->level_embeds, &e->conv_w[0], &e->conv_w[1],
@@ -654,7 +656,7 @@ int occb200_engine_finalize(occb200_engine* e)
             return 0;
         };
         auto up_cat = [&](DevBuf& wbuf, DevBuf& bbuf, DevBuf* wh, const std::string& n1, const std::string& n2,
-                          size_t r1, size_t r2, size_t k, DevBuf* fold = nullptr) -> int {
+                          size_t r1, size_t r2, size_t k, DevBuf* fold = nullptr, DevBuf* fold_const = nullptr) -> int {
             const std::vector<float>* W1 = find(e, n1 + ".weight", r1 * k);
             const std::vector<float>* B1 = find(e, n1 + ".bias", r1);
             const std::vector<float>* W2 = find(e, n2 + ".weight", r2 * k);
@@ -666,12 +668,23 @@ int occb200_engine_finalize(occb200_engine* e)
             if (upload(wbuf, W.data(), W.size()) || upload(bbuf, B.data(), B.size())) return 2;
             if (tc && wh && upload_bf16(*wh, W.data(), W.size())) return 2;
             if (tc32 && wh && upload_w3(*wh, W.data(), r1 + r2, k)) return 2;
-            if (tc && fold) {                                    // k = 2C: fold the first half of every row into (W1 + W2)
-                std::vector<float> Wf(W);
-                const size_t half = k / 2;
-                for (size_t r = 0; r < r1 + r2; ++r)
-                    for (size_t j = 0; j < half; ++j) Wf[r * k + j] = W[r * k + j] + W[r * k + half + j];
+            if (tc && fold) {                                    // k = 2C: (W1 + W2) [r, C] bf16 and the constant W2 pos + b
+                const size_t half = k / 2, rows = r1 + r2;
+                std::vector<float> Wf(rows * half), W2h(rows * half);
+                for (size_t r = 0; r < rows; ++r)
+                    for (size_t j = 0; j < half; ++j) {
+                        Wf[r * half + j] = W[r * k + j] + W[r * k + half + j];
+                        W2h[r * half + j] = W[r * k + half + j];
+                    }
                 if (upload_bf16(*fold, Wf.data(), Wf.size())) return 2;
+                DevBuf w2;
+                if (upload(w2, W2h.data(), W2h.size())) return 2;
+                if (fold_const->alloc((size_t)Nq * rows * 4)) return 2;
+                if (gemm_simt<float, float>(e->pos.as<float>(), (int)half, nullptr, 0, (int)half, w2.as<float>(), bbuf.as<float>(),
+                                            nullptr, (int)rows, fold_const->as<float>(), (int)rows, Nq, (int)rows, (int)half,
+                                            ACT_NONE, 0)) return 2;
+                OCC_CUDA(cudaDeviceSynchronize());
+                w2.release();
             }
             return 0;
         };
@@ -680,7 +693,7 @@ int occb200_engine_finalize(occb200_engine* e)
         const size_t sq_off = 8 * c.num_levels * c.sca_points * 2, sq_w = 8 * c.num_levels * c.sca_points;
         if ((rc = up(w.tsa_v_w, w.tsa_v_b, &w.tsa_v_wh, a0 + ".value_proj", C, C))) return rc;
         if ((rc = up_cat(w.tsa_q_w, w.tsa_q_b, &w.tsa_q_wh, a0 + ".sampling_offsets", a0 + ".attention_weights", tq_off,
-                         tq_w, 2 * C, &w.tsa_q_wh_fold))) return rc;
+                         tq_w, 2 * C, &w.tsa_q_wh_fold, &w.tsa_q_const))) return rc;
         if ((rc = up(w.tsa_o_w, w.tsa_o_b, &w.tsa_o_wh, a0 + ".output_proj", C, C))) return rc;
         if ((rc = up_cat(w.sca_q_w, w.sca_q_b, &w.sca_q_wh, d + ".sampling_offsets", d + ".attention_weights", sq_off,
                          sq_w, C))) return rc;

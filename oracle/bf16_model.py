@@ -19,7 +19,8 @@ Storage points emulated (bf16 unless noted), single frame (batch 1):
   gather outputs (TSA after the queue mean, SCA after /count), FFN hidden, voxel features, head hidden
   the fp32 residual stream / LayerNorm / logits / flow stay fp32
   self mode (prev_bev None): sampling_offsets/attention_weights of TSA see cat([q, q+pos]); the engine
-  computes it as [q | pos] . [W1+W2 | W2]^T with the folded weight rounded to bf16 (same here)
+  computes it as q . (W1+W2)^T + [pos . W2^T + b] with the folded weight rounded to bf16 and the bracket a
+  per-layer fp32 constant computed once from the parameters (same here)
 SCA sampling location: the engine evaluates u*W + (dx - 0.5) with one rounding (fma) instead of
 (u + dx/W)*W - 0.5; emulated in float64.
 
@@ -166,9 +167,8 @@ def encoder(qz, p, cfg, feats, img_metas, prev_bev=None):
         bq = torch.cat([p[a0 + '.sampling_offsets.bias'], p[a0 + '.attention_weights.bias']], 0)
         if has_prev:                                                               # cat([value[:bs] = prev_bev, q + pos])
             qp = F.linear(torch.cat([prev_t, q_pos_t], -1), qz.bf(Wq), bq)
-        elif qz.quant:                                                             # folded: [q | pos] . [W1+W2 | W2]^T
-            Wf = torch.cat([Wq[:, :C] + Wq[:, C:], Wq[:, C:]], 1)
-            qp = F.linear(torch.cat([q_t, pos_t], -1), qz.bf(Wf), bq)
+        elif qz.quant:                                                             # folded: q . (W1+W2)^T + [pos . W2^T + b]
+            qp = F.linear(q_t, qz.bf(Wq[:, :C] + Wq[:, C:])) + F.linear(pos, Wq[:, C:], bq)   # bracket: fp32 constant
         else:
             qp = F.linear(torch.cat([q_t, q_pos_t], -1), Wq, bq)
         attn = tsa_gather(qz, cfg, v_prev, v_cur, qz.hf(qp), bev_h, bev_w)
