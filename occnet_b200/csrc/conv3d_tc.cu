@@ -5,12 +5,15 @@
 // Tensors are channels-last bf16 [X][Y][Z][C] (see decoder_simt.cu for the layout rationale).
 //   M tile  = 128 voxels = 8 (y) x 16 (z, the whole pillar) at one x
 //   N       = 32 output channels,  K = 27 taps x Cin
-// im2col is done by TMA: one 4-D box load {Cin, 16 z, 8 y, 1 x} per tap with the tap's (dz,dy,dx) offset
-// in the coordinates; out-of-bounds rows are zero-filled by the TMA unit, which IS the conv's zero padding
-// (including the z = -1 / z = 16 halo).  All 27 weight tiles stay resident in shared memory.
+// im2col is done by TMA: one 4-D box load {Cin, 16 z, 8 + 2 y, 1 x} per (plane, dz) with the dz offset in the
+// coordinates and a one-row y halo on both sides, so the three dy shifts are SUB-VIEWS of the same shared-memory tile
+// (row offset dy * 16, a multiple of the 8-row swizzle atom); out-of-bounds rows are zero-filled by the TMA unit, which
+// IS the conv's zero padding (including the z = -1 / z = 16 halo).  All 27 weight tiles stay resident in shared memory.
 //   warp 0: TMA producer (8-stage ring)    warp 1: tcgen05.mma issuer (plane-major: each loaded tile feeds the
 //   dx = 0/1/2 taps of three neighbouring outputs through ONE N = 96 MMA into adjacent TMEM slots, ring of 8)
 //   warps 2-5: epilogue (tcgen05.ld -> +bias -> ReLU -> bf16 -> 64-byte rows, contiguous 8 KB per tile)
+#include <cstdlib>
+
 #include "common.cuh"
 #include "conv3d_tc.cuh"
 #include "tc_common.cuh"
@@ -20,6 +23,7 @@ namespace occ {
 namespace {
 
 constexpr int STAGES = 8, TILE_Y = 8, TILE_Z = 16, BLOCK_M = 128, COUT = 32, TAPS = 27, SLOTS = 8;
+constexpr int HALO_ROWS = (TILE_Y + 2) * TILE_Z;          // rows of one staged tile: y0-1 .. y0+8, all 16 z
 constexpr int NUM_THREADS = 192;
 constexpr int BAR_BYTES = 512;
 
@@ -33,13 +37,18 @@ constexpr int BAR_BYTES = 512;
 // accumulates and the issue loop has no per-output special cases.
 // Each CTA owns a contiguous range of the (y_tile, x) tile sequence, cut into segments of constant y_tile; a segment
 // [xa, xb) streams the planes max(xa-1,0) .. min(xb, X-1).
-template <int CIN>
+// UNI: the producer / issuer warps run their loops with ALL 32 lanes (lane 0 alone executes the TMA / MMA / commit
+// instructions): loop counters, stage indices and UMMA descriptors are then warp-uniform values the compiler keeps in the
+// uniform datapath, instead of per-lane registers that need an R2UR move in front of every tcgen05.mma operand (ncu of the
+// single-lane version: 1.8 M R2UR + 1.3 M IMAD around 0.19 M MMAs; the issuing thread, not the tensor pipe, was the limiter).
+template <int CIN, bool UNI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
                  const float* __restrict__ bias, bf16* __restrict__ out, int X, int Y)
 {
     constexpr int ROW_BYTES = CIN * 2;                       // 32 (SWIZZLE_32B) or 64 (SWIZZLE_64B)
-    constexpr int A_BYTES = BLOCK_M * ROW_BYTES;             // 4 / 8 KB per stage
+    constexpr int A_BYTES = HALO_ROWS * ROW_BYTES;           // 5 / 10 KB per stage (three dy sub-views of 128 rows)
+    constexpr int DY_BYTES = TILE_Z * ROW_BYTES;             // one y row of the tile
     constexpr int W_TAP_BYTES = COUT * ROW_BYTES;            // 1 / 2 KB per tap
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -72,11 +81,14 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+    const bool leader = lane == 0;
     if (warp == 0) {
-        if (lane == 0) {
-            tc::mbar_arrive_expect_tx(w_bar, TAPS * W_TAP_BYTES);
-            for (int t = 0; t < TAPS; ++t)                   // global tap order is (dz,dy,dx); resident order (dz,dy,2-dx)
-                tc::tma_load_2d(w_base + ((t / 3) * 3 + (2 - t % 3)) * W_TAP_BYTES, &tmW, w_bar, 0, t * COUT);
+        if (UNI || leader) {
+            if (leader) {
+                tc::mbar_arrive_expect_tx(w_bar, TAPS * W_TAP_BYTES);
+                for (int t = 0; t < TAPS; ++t)               // global tap order is (dz,dy,dx); resident order (dz,dy,2-dx)
+                    tc::tma_load_2d(w_base + ((t / 3) * 3 + (2 - t % 3)) * W_TAP_BYTES, &tmW, w_bar, 0, t * COUT);
+            }
             int s = 0; uint32_t ph = 0;
             for (int t = t_begin; t < t_end;) {
                 const int yt = t / X, xa = t % X;
@@ -84,11 +96,12 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
                 const int y0 = yt * TILE_Y;
                 const int p_lo = max(xa - 1, 0), p_hi = min(xb, X - 1);
                 for (int p = p_lo; p <= p_hi; ++p) {
-                    for (int t9 = 0; t9 < 9; ++t9) {
-                        const int dz = t9 / 3, dy = t9 % 3;
+                    for (int dz = 0; dz < 3; ++dz) {
                         tc::mbar_wait(empty_bar(s), ph ^ 1);
-                        tc::mbar_arrive_expect_tx(full_bar(s), A_BYTES);
-                        tc::tma_load_4d(a_base + s * A_BYTES, &tmIn, full_bar(s), 0, dz - 1, y0 + dy - 1, p);
+                        if (leader) {
+                            tc::mbar_arrive_expect_tx(full_bar(s), A_BYTES);
+                            tc::tma_load_4d(a_base + s * A_BYTES, &tmIn, full_bar(s), 0, dz - 1, y0 - 1, p);
+                        }
                         if (++s == STAGES) { s = 0; ph ^= 1; }
                     }
                 }
@@ -96,7 +109,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (UNI || leader) {
             const uint32_t idesc1 = tc::make_idesc_bf16(BLOCK_M, COUT), idesc2 = tc::make_idesc_bf16(BLOCK_M, 2 * COUT),
                            idesc3 = tc::make_idesc_bf16(BLOCK_M, 3 * COUT);
             auto idesc_of = [&](int outputs) { return outputs == 1 ? idesc1 : (outputs == 2 ? idesc2 : idesc3); };
@@ -123,24 +136,31 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
                     tc::tc_fence_after();
                     const uint32_t d0 = tmem_base + slot_lo * COUT;
                     const uint32_t i_first = idesc_of(first), i_rest = idesc_of(cnt - first);
-                    for (int t9 = 0; t9 < 9; ++t9) {
+                    for (int dz = 0; dz < 3; ++dz) {
                         tc::mbar_wait(full_bar(s), ph);
                         tc::tc_fence_after();
-                        const uint64_t da = da0 + (uint64_t)((s * A_BYTES) >> 4);
-                        const uint64_t db = db0 + (uint64_t)(((t9 * 3 + off) * W_TAP_BYTES) >> 4);
+                        if (leader) {
 #pragma unroll
-                        for (int k = 0; k < CIN / 16; ++k) {
-                            tc::umma_bf16(d0, da + 2 * k, db + 2 * k, i_first, 1);
-                            if (first < cnt)
-                                tc::umma_bf16(tmem_base, da + 2 * k, db + (uint64_t)((first * W_TAP_BYTES) >> 4) + 2 * k, i_rest, 1);
+                            for (int dy = 0; dy < 3; ++dy) {
+                                const int t9 = dz * 3 + dy;
+                                const uint64_t da = da0 + (uint64_t)((s * A_BYTES + dy * DY_BYTES) >> 4);
+                                const uint64_t db = db0 + (uint64_t)(((t9 * 3 + off) * W_TAP_BYTES) >> 4);
+#pragma unroll
+                                for (int k = 0; k < CIN / 16; ++k) {
+                                    tc::umma_bf16(d0, da + 2 * k, db + 2 * k, i_first, 1);
+                                    if (first < cnt)
+                                        tc::umma_bf16(tmem_base, da + 2 * k, db + (uint64_t)((first * W_TAP_BYTES) >> 4) + 2 * k, i_rest, 1);
+                                }
+                            }
+                            tc::umma_commit(empty_bar(s));
                         }
-                        tc::umma_commit(empty_bar(s));
+                        if (UNI) __syncwarp();
                         if (++s == STAGES) { s = 0; ph ^= 1; }
                     }
                     // outputs whose last plane this was: x = p-1 (and x = X-1 on the last plane)
                     for (int x = x_lo; x <= x_hi; ++x) {
                         if (min(x + 1, X - 1) != p) continue;
-                        tc::umma_commit(tfull_bar((n_base + (x - xa)) & (SLOTS - 1)));
+                        if (leader) tc::umma_commit(tfull_bar((n_base + (x - xa)) & (SLOTS - 1)));
                     }
                 }
                 n_base += xb - xa;
@@ -211,7 +231,7 @@ int launch_conv3d_tc(const bf16* in, const bf16* w_tap_major, const float* bias,
     {
         const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Z, (uint64_t)Y, (uint64_t)X};
         const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)Z * Cin * 2, (uint64_t)Y * Z * Cin * 2};
-        const uint32_t box[4] = {(uint32_t)Cin, (uint32_t)TILE_Z, (uint32_t)TILE_Y, 1u};
+        const uint32_t box[4] = {(uint32_t)Cin, (uint32_t)TILE_Z, (uint32_t)(TILE_Y + 2), 1u};
         if (make_tensor_map_bf16(&tmIn, in, 4, dims, strides, box, row_bytes)) return 1;
     }
     {
@@ -220,18 +240,20 @@ int launch_conv3d_tc(const bf16* in, const bf16* w_tap_major, const float* bias,
         const uint32_t box[2] = {(uint32_t)Cin, (uint32_t)COUT};
         if (make_tensor_map_bf16(&tmW, w_tap_major, 2, dims, strides, box, row_bytes)) return 1;
     }
-    const int a_bytes = BLOCK_M * row_bytes, w_bytes = (TAPS * COUT * row_bytes + 1023) & ~1023;
+    const int a_bytes = HALO_ROWS * row_bytes, w_bytes = (TAPS * COUT * row_bytes + 1023) & ~1023;
     const int smem = 1024 + w_bytes + STAGES * a_bytes + BAR_BYTES;
     const int num_sms = sm_count_current_device();
     const int tiles = X * ((Y + TILE_Y - 1) / TILE_Y);
     const int grid = tiles < num_sms ? tiles : num_sms;
-    if (Cin == 16) {
-        OCC_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        conv3d_tc_kernel<16><<<grid, NUM_THREADS, smem, stream>>>(tmIn, tmW, bias, out, X, Y);
-    } else {
-        OCC_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        conv3d_tc_kernel<32><<<grid, NUM_THREADS, smem, stream>>>(tmIn, tmW, bias, out, X, Y);
-    }
+    static const bool uni = getenv("OCC_CONV_SINGLE_LANE") == nullptr;      // OCC_CONV_SINGLE_LANE=1: the lane-0-only loops
+#define OCC_CONV_LAUNCH(C, U)                                                                                          \
+    do {                                                                                                               \
+        OCC_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<C, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));     \
+        conv3d_tc_kernel<C, U><<<grid, NUM_THREADS, smem, stream>>>(tmIn, tmW, bias, out, X, Y);                       \
+    } while (0)
+    if (Cin == 16) { if (uni) OCC_CONV_LAUNCH(16, true); else OCC_CONV_LAUNCH(16, false); }
+    else           { if (uni) OCC_CONV_LAUNCH(32, true); else OCC_CONV_LAUNCH(32, false); }
+#undef OCC_CONV_LAUNCH
     OCC_CUDA(cudaGetLastError());
     return 0;
 }
