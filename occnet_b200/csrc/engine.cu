@@ -328,12 +328,23 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
         } else {
         T* v_cur = e->tsa_value.as<T>();
         T* v_prev = v_cur;
-        if (gemm<T, T>(e, has_prev ? q0_t : q_in, nullptr, 0, w.tsa_v_w.as<float>(), w.tsa_v_wh.p,
-                       w.tsa_v_b.as<float>(), nullptr, v_cur, Nq, C, C, ACT_NONE, st)) return 2;
+        // head-major value maps + pair-fetch gather on the fused tensor-core path (same layout trick as the SCA values)
+        static const bool tsa_rowmajor_env = getenv("OCC_TSA_ROWMAJOR") != nullptr;
+        const bool tsa_hm = fuse_ln && e->value_head_major && q_half && !tsa_rowmajor_env;
+        auto value_gemm = [&](const T* a, T* dst) -> int {
+            if (tsa_hm) {
+                e->launches++;
+                ProfScope ps(e, st, CAT_GEMM);
+                return gemm_tc_heads256(reinterpret_cast<const bf16*>(a), w.tsa_v_wh.as<bf16>(), w.tsa_v_b.as<float>(),
+                                        reinterpret_cast<bf16*>(dst), Nq, C, st);
+            }
+            return gemm<T, T>(e, a, nullptr, 0, w.tsa_v_w.as<float>(), w.tsa_v_wh.p, w.tsa_v_b.as<float>(), nullptr, dst, Nq, C, C,
+                              ACT_NONE, st);
+        };
+        if (value_gemm(has_prev ? q0_t : q_in, v_cur)) return 2;
         if (has_prev) {
             v_prev = e->tsa_value_prev.as<T>();
-            if (gemm<T, T>(e, e->prev_t.as<T>(), nullptr, 0, w.tsa_v_w.as<float>(), w.tsa_v_wh.p,
-                           w.tsa_v_b.as<float>(), nullptr, v_prev, Nq, C, C, ACT_NONE, st)) return 2;
+            if (value_gemm(e->prev_t.as<T>(), v_prev)) return 2;
         }
         if (fold_pos) {
             if (gemm<T, __half>(e, q_in, nullptr, 0, w.tsa_q_w.as<float>(), w.tsa_q_wh_fold.p, nullptr,
@@ -348,7 +359,10 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
         }
         {
             ProfScope ps(e, st, CAT_TSA);
-            if (launch_tsa_fused<T>(v_prev, v_cur, qproj, q_half, c.bev_h, c.bev_w, attn_out, st)) return 2;
+            if (tsa_hm) {
+                if (launch_tsa_pair(reinterpret_cast<const bf16*>(v_prev), reinterpret_cast<const bf16*>(v_cur), qproj, q_half,
+                                    c.bev_h, c.bev_w, reinterpret_cast<bf16*>(attn_out), st)) return 2;
+            } else if (launch_tsa_fused<T>(v_prev, v_cur, qproj, q_half, c.bev_h, c.bev_w, attn_out, st)) return 2;
         }
         e->launches++;
         if (fuse_ln) {

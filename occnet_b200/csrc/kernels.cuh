@@ -27,6 +27,8 @@ int launch_tsa_fused(const T* value_prev, const T* value_cur, const void* qproj,
 template <typename T>
 int launch_sca_fused(const T* value, const void* qproj, bool qproj_is_half, const ScaParams& sp, const LevelGeom& lg, int Nv,
                      T* out, uint8_t* hits, cudaStream_t stream);
+int launch_tsa_pair(const bf16* value_prev_hm, const bf16* value_cur_hm, const void* qproj, bool qproj_is_half, int bev_h,
+                    int bev_w, bf16* out, cudaStream_t stream);
 // same gather on head-major value maps [8 heads][num_cams*Nv tokens][32] (pair-fetch kernel, bf16 production path)
 int launch_sca_pair(const bf16* value_hm, const void* qproj, bool qproj_is_half, const ScaParams& sp, const LevelGeom& lg,
                     int Nv, bf16* out, uint8_t* hits, cudaStream_t stream);

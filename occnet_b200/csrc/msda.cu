@@ -608,6 +608,65 @@ tsa_fused_kernel(const T* __restrict__ value_prev, const T* __restrict__ value_c
 }
 
 // ------------------------------------------------------------------------------------------
+// Pair-fetch variant of the temporal gather on head-major value maps [8 heads][Nq][32] bf16 (see sca_pair_kernel):
+// phase 1: lane (head, s) prepares its two samples (queue s/2, points 2(s%2), 2(s%2)+1) as shared-memory descriptors
+// [sample = queue*4 + point][head]; phase 2: lane (hl, side, slice) gathers {left | right} pixel pairs for heads hl, 4+hl.
+template <typename QT>
+__global__ void __launch_bounds__(256)
+tsa_pair_kernel(const bf16* __restrict__ value_prev_hm, const bf16* __restrict__ value_cur_hm, const QT* __restrict__ qproj,
+                int bev_h, int bev_w, bf16* __restrict__ out)
+{
+    __shared__ uint4 descs[8][8 * 8];                            // [warp][sample][head]
+    const int q = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int Nq = bev_h * bev_w;
+    if (q >= Nq) return;
+    const int lane = threadIdx.x & 31, head = lane >> 2, s = lane & 3;
+    const int hl = lane >> 3, j = lane & 7, side = j >> 2;
+    const int qu_own = s >> 1, p0 = (s & 1) * 2;
+    const QT* qp = qproj + (int64_t)q * 192;
+    float offv[4], lgv[2];
+    load_q<4>(qp + head * 16 + qu_own * 8 + p0 * 2, offv);
+    load_q<2>(qp + 128 + head * 8 + qu_own * 4 + p0, lgv);
+    float mx = fmaxf(lgv[0], lgv[1]);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    const float e0 = expf(lgv[0] - mx), e1 = expf(lgv[1] - mx);
+    float sum = e0 + e1;
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    const float wt0 = e0 / sum, wt1 = e1 / sum;
+    const float fw = (float)bev_w, fh = (float)bev_h;
+    const float rx = __fdiv_rn((float)(q % bev_w) + 0.5f, fw);
+    const float ry = __fdiv_rn((float)(q / bev_w) + 0.5f, fh);
+    const float wim0 = __fadd_rn(rx, __fdiv_rn(offv[0], fw)) * fw - 0.5f;
+    const float him0 = __fadd_rn(ry, __fdiv_rn(offv[1], fh)) * fh - 0.5f;
+    const float wim1 = __fadd_rn(rx, __fdiv_rn(offv[2], fw)) * fw - 0.5f;
+    const float him1 = __fadd_rn(ry, __fdiv_rn(offv[3], fh)) * fh - 0.5f;
+    uint4* dw = descs[threadIdx.x >> 5];
+    dw[(qu_own * 4 + p0) * 8 + head] = make_desc(prep_sample(him0, wim0, wt0, bev_h, bev_w));
+    dw[(qu_own * 4 + p0 + 1) * 8 + head] = make_desc(prep_sample(him1, wim1, wt1, bev_h, bev_w));
+    __syncwarp();
+    float acc0[8], acc1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc0[i] = 0.f; acc1[i] = 0.f; }
+    const int64_t plane = (int64_t)Nq * 32;
+    const bf16* p0v = value_prev_hm + (int64_t)hl * plane + j * 8;
+    const bf16* c0v = value_cur_hm + (int64_t)hl * plane + j * 8;
+    gather_descs_pair<8, 2>(acc0, dw + hl, side, [&](int i, const bf16*& base, int& W) { base = i < 4 ? p0v : c0v; W = bev_w; });
+    gather_descs_pair<8, 2>(acc1, dw + 4 + hl, side,
+                            [&](int i, const bf16*& base, int& W) { base = (i < 4 ? p0v : c0v) + 4 * plane; W = bev_w; });
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        acc0[i] += __shfl_xor_sync(0xffffffffu, acc0[i], 4);
+        acc1[i] += __shfl_xor_sync(0xffffffffu, acc1[i], 4);
+    }
+    if (side == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { acc0[i] *= 0.5f; acc1[i] *= 0.5f; }
+        store8(out + (int64_t)q * 256 + hl * 32 + j * 8, acc0);
+        store8(out + (int64_t)q * 256 + (4 + hl) * 32 + j * 8, acc1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Camera projection of one pillar point (encoder.py:104-139), fp32, same operation order.
 __device__ __forceinline__ void project_point(const float* __restrict__ m /*4x4 row-major*/, float xs, float ys,
                                               float zs, const ScaParams& sp, float& u, float& v, bool& ok)
@@ -810,6 +869,17 @@ template int launch_sca_fused<float>(const float*, const void*, bool, const ScaP
                                      uint8_t*, cudaStream_t);
 template int launch_sca_fused<bf16>(const bf16*, const void*, bool, const ScaParams&, const LevelGeom&, int, bf16*,
                                     uint8_t*, cudaStream_t);
+
+int launch_tsa_pair(const bf16* value_prev_hm, const bf16* value_cur_hm, const void* qproj, bool q_half, int bev_h, int bev_w,
+                    bf16* out, cudaStream_t stream)
+{
+    OCC_CHECK(bev_h >= 2 && bev_w >= 2, "tsa_pair: the BEV grid must be at least 2x2");
+    const dim3 grid(ceil_div(bev_h * bev_w, 8));
+    if (q_half) tsa_pair_kernel<__half><<<grid, 256, 0, stream>>>(value_prev_hm, value_cur_hm, (const __half*)qproj, bev_h, bev_w, out);
+    else        tsa_pair_kernel<float><<<grid, 256, 0, stream>>>(value_prev_hm, value_cur_hm, (const float*)qproj, bev_h, bev_w, out);
+    OCC_CUDA(cudaGetLastError());
+    return 0;
+}
 
 int launch_sca_pair(const bf16* value_hm, const void* qproj_v, bool q_half, const ScaParams& sp, const LevelGeom& lg, int Nv,
                     bf16* out, uint8_t* hits, cudaStream_t stream)
