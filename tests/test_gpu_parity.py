@@ -319,7 +319,8 @@ import torch, ctypes
 from occnet_b200 import _lib
 lib = _lib.load()
 torch.manual_seed(0)
-for (M, N, K) in [(128, 256, 256), (1000, 192, 512), (40000, 256, 256), (4100, 768, 256), (333, 512, 256)]:
+for (M, N, K) in [(128, 256, 256), (1000, 192, 512), (40000, 256, 256), (4100, 768, 256), (333, 512, 256),
+                  (2000, 256, 768), (777, 192, 1536), (1000, 192, 256)]:      # K > 512: streamed (non-resident) weight tiles
     A = (torch.randn(M, K, device='cuda') * 0.5).bfloat16()
     W = (torch.randn(N, K, device='cuda') * 0.1).bfloat16()
     b = torch.randn(N, device='cuda')
