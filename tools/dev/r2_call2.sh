@@ -21,7 +21,10 @@ timeout 1500 python tools/dev/ab.py base= rowmajor=OCC_VALUE_ROWMAJOR:1 tsa_row=
     fp32simt=AB_PRECISION:fp32,AB_TC:0,AB_FRAMES:20 > gpurun_out/c2_ab.log 2>&1
 cat gpurun_out/c2_ab.log | cut -c1-400
 timeout 600 python tools/dev/lanes_exp.py > gpurun_out/c2_lanes.log 2>&1; cat gpurun_out/c2_lanes.log | tail -4
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 80 --csv --log-file gpurun_out/c2_launches.csv \
+AB_FRAMES=3 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 228 -c 120 --csv --log-file gpurun_out/c2_launches.csv \
     python tools/dev/ab_one.py > gpurun_out/c2_ncu_list.log 2>&1
 tail -2 gpurun_out/c2_ncu_list.log
+AB_FRAMES=3 timeout 900 ncu --set full --clock-control none --import-source on -s 114 -c 57 -o gpurun_out/c2_prof_frame \
+    python tools/dev/ab_one.py > gpurun_out/c2_ncu_full.log 2>&1
+tail -2 gpurun_out/c2_ncu_full.log; ls -la gpurun_out/*.ncu-rep
 du -sh gpurun_out
