@@ -103,9 +103,10 @@ int occb200_engine_set_cameras(occb200_engine* e, const float* cam_mat, const fl
  * passed UN-rotated to occb200_engine_forward.  NULL clears it (prev_bev is taken as already rotated).  Synchronous. */
 int occb200_engine_set_prev_rotation(occb200_engine* e, const int32_t* map_host);
 
-/* Element type of the feature levels handed to _forward / _forward_host / _submit_host from now on: 0 = fp32 (default,
- * the reference's dtype), 1 = bf16 (same [num_cams, C, h, w] layout, pointers passed through the same arguments): what
- * an on-device backbone emits, and half the PCIe bytes for host pipelines that already hold bf16 features. */
+/* Element type / layout of the feature levels handed to _forward / _forward_host / _submit_host from now on (pointers
+ * travel through the same arguments): 0 = fp32 [num_cams, C, h, w] (default, the reference's), 1 = bf16, same layout
+ * (half the PCIe bytes for host pipelines that hold bf16 features), 2 = bf16 channels-last [num_cams, h, w, C] -- the
+ * native output of occb200_backbone_forward_nhwc_bf16, so images -> voxels never leaves the device or transposes. */
 int occb200_engine_set_input_dtype(occb200_engine* e, int feats_bf16);
 
 /* One frame, DEVICE buffers.
@@ -184,8 +185,8 @@ int occb200_gemm_bf16_tc(const void* A_bf16, const void* W_bf16, const float* bi
                          void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Image backbone + neck (the step immediately BEFORE the hot path).  FIRST VERSION: builds for
- * sm_100a, not yet validated on a GPU (round-1 GPU budget was spent); parity tests are opt-in (OCC_EXPERIMENTAL=1).
+ * Image backbone + neck (the step immediately BEFORE the hot path); parity vs its oracle:
+ * tests/test_backbone_gpu.py (fp32 1e-3 relative to the feature magnitude, bf16 bars stated there).
  * Replaces `self.img_backbone(img)` + `self.img_neck(...)` in BEVFormerOcc.extract_img_feat
  * (detectors/bevformer_occ.py:66-99) for the shipped configuration (bevformer_base_occ.py:48-66): mmdet
  * ResNet(depth=50, out_indices=(1,2,3), style='pytorch', norm_eval=True) + FPN(in_channels=[512,1024,2048],
@@ -203,6 +204,10 @@ int occb200_backbone_finalize(occb200_backbone* e);
 int occb200_backbone_level_shape(const occb200_backbone* e, int level, int* h, int* w);
 int occb200_backbone_forward(occb200_backbone* e, const float* img, float* out0, float* out1, float* out2, float* out3,
                              void* stream);
+/* Same, precision 1 only: the four FPN outputs are written as bf16 channels-last [num_images, h_l, w_l, 256] straight by
+ * the last convolutions (no NCHW fp32 copy): the layout occb200_engine_set_input_dtype(e, 2) consumes. */
+int occb200_backbone_forward_nhwc_bf16(occb200_backbone* e, const float* img, void* out0, void* out1, void* out2, void* out3,
+                                       void* stream);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,7 @@ SIGNATURES = {
     'occb200_backbone_finalize': (_i, [_vp]),
     'occb200_backbone_level_shape': (_i, [_vp, _i, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     'occb200_backbone_forward': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'occb200_backbone_forward_nhwc_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

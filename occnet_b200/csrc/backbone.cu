@@ -178,8 +178,9 @@ int conv(occb200_backbone* e, const T* in, int N, int H, int W, const ConvW& c, 
     return conv_gemm<T>(e, A, M, c, out, act, st);
 }
 
+// nhwc_out != nullptr (bf16 only): the FPN output convolutions write the caller's channels-last buffers directly
 template <typename T>
-int forward_impl(occb200_backbone* e, const float* img, float* const* outs, cudaStream_t st)
+int forward_impl(occb200_backbone* e, const float* img, float* const* outs, cudaStream_t st, void* const* nhwc_out = nullptr)
 {
     const int N = e->num_images;
     int H = e->H, W = e->W, Ho, Wo;
@@ -230,9 +231,12 @@ int forward_impl(occb200_backbone* e, const float* img, float* const* outs, cuda
         if (launch_upsample_add_nhwc<T>(e->lat[i - 1].as<T>(), e->lat[i].as<T>(), N, lh[i - 1], lw[i - 1], lh[i], lw[i],
                                         e->out_channels, st)) return 2;
     int oh[4], ow[4];
+    T* fo[4];
+    for (int i = 0; i < 4; ++i) fo[i] = (nhwc_out && nhwc_out[i]) ? reinterpret_cast<T*>(nhwc_out[i]) : e->fo[i].as<T>();
     for (int i = 0; i < 3; ++i)
-        if (conv<T>(e, e->lat[i].as<T>(), N, lh[i], lw[i], e->fpnc[i], e->fo[i].as<T>(), ACT_NONE, oh[i], ow[i], st)) return 2;
-    if (conv<T>(e, e->fo[2].as<T>(), N, oh[2], ow[2], e->fpnc[3], e->fo[3].as<T>(), ACT_NONE, oh[3], ow[3], st)) return 2;
+        if (conv<T>(e, e->lat[i].as<T>(), N, lh[i], lw[i], e->fpnc[i], fo[i], ACT_NONE, oh[i], ow[i], st)) return 2;
+    if (conv<T>(e, fo[2], N, oh[2], ow[2], e->fpnc[3], fo[3], ACT_NONE, oh[3], ow[3], st)) return 2;
+    if (nhwc_out) return 0;
     for (int i = 0; i < 4; ++i)
         if (outs[i] && launch_nhwc_to_nchw_f32<T>(e->fo[i].as<T>(), outs[i], N, oh[i] * ow[i], e->out_channels, st)) return 2;
     return 0;
@@ -363,6 +367,16 @@ int occb200_backbone_forward(occb200_backbone* e, const float* img, float* out0,
     float* outs[4] = {out0, out1, out2, out3};
     return e->precision ? forward_impl<bf16>(e, img, outs, (cudaStream_t)stream)
                         : forward_impl<float>(e, img, outs, (cudaStream_t)stream);
+}
+
+int occb200_backbone_forward_nhwc_bf16(occb200_backbone* e, const float* img, void* out0, void* out1, void* out2, void* out3,
+                                       void* stream)
+{
+    OCC_CHECK(e && img && out0 && out1 && out2 && out3, "null pointer");
+    OCC_CHECK(e->finalized, "backbone_finalize() has not been called");
+    OCC_CHECK(e->precision == 1, "backbone_forward_nhwc_bf16 needs a bf16 backbone (precision 1)");
+    void* outs[4] = {out0, out1, out2, out3};
+    return forward_impl<bf16>(e, img, nullptr, (cudaStream_t)stream, outs);
 }
 
 }  // extern "C"

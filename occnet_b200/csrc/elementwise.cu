@@ -345,3 +345,55 @@ int launch_gather_rows(const float* src, const int32_t* map, int rows, int C, T*
 template int launch_gather_rows<float>(const float*, const int32_t*, int, int, float*, float*, cudaStream_t);
 template int launch_gather_rows<bf16>(const float*, const int32_t*, int, int, bf16*, float*, cudaStream_t);
 }  // namespace occ
+
+// ---- feature packing from channels-last bf16 levels [num_cams, h, w, C] (what occb200_backbone_forward_nhwc_bf16 writes):
+//      no transpose left -- tokens[cam][start_l + p][:] = feat_l[cam][p][:] + cams_embeds[cam] + level_embeds[l]
+namespace occ {
+namespace {
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_levels_nhwc_kernel(PackLevels pl, const float* __restrict__ cams_embeds, const float* __restrict__ level_embeds, int C,
+                        int Nv, int num_cams, T* __restrict__ tokens)
+{
+    const int per_row = C >> 3;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)num_cams * Nv * per_row) return;
+    const int c8 = (int)(i % per_row) * 8;
+    const int64_t row = i / per_row;                            // cam * Nv + token
+    const int cam = (int)(row / Nv), tok = (int)(row % Nv);
+    int lvl = 0;
+#pragma unroll
+    for (int l = 1; l < 8; ++l) if (l < pl.num_levels && tok >= pl.start[l]) lvl = l;
+    const void* feat_v = nullptr; int hw = 0, start = 0;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) if (l == lvl) { feat_v = pl.feat[l]; hw = pl.hw[l]; start = pl.start[l]; }
+    const bf16* src = reinterpret_cast<const bf16*>(feat_v) + ((int64_t)cam * hw + (tok - start)) * C + c8;
+    float v[8];
+    load8(src, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float x = v[k];
+        if (cams_embeds) x = x + cams_embeds[cam * C + c8 + k];
+        v[k] = x + level_embeds[lvl * C + c8 + k];
+    }
+    store8(tokens + row * C + c8, v);
+}
+}  // namespace
+template <typename T>
+int launch_pack_levels_nhwc(const void* const* feats, const LevelGeom& lg, const float* cams_embeds, const float* level_embeds,
+                            int num_cams, int C, int Nv, T* tokens, cudaStream_t stream)
+{
+    OCC_CHECK(C % 8 == 0 && lg.num_levels >= 1 && lg.num_levels <= 8, "pack_levels_nhwc: C % 8, 1..8 levels");
+    PackLevels pl{};
+    pl.num_levels = lg.num_levels;
+    for (int l = 0; l < lg.num_levels; ++l) { pl.feat[l] = feats[l]; pl.hw[l] = lg.h[l] * lg.w[l]; pl.start[l] = lg.start[l]; }
+    const int64_t n = (int64_t)num_cams * Nv * (C >> 3);
+    pack_levels_nhwc_kernel<T><<<ceil_div(n, 256), 256, 0, stream>>>(pl, cams_embeds, level_embeds, C, Nv, num_cams, tokens);
+    OCC_CUDA(cudaGetLastError());
+    return 0;
+}
+template int launch_pack_levels_nhwc<float>(const void* const*, const LevelGeom&, const float*, const float*, int, int, int, float*,
+                                            cudaStream_t);
+template int launch_pack_levels_nhwc<bf16>(const void* const*, const LevelGeom&, const float*, const float*, int, int, int, bf16*,
+                                           cudaStream_t);
+}  // namespace occ

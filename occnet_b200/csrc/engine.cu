@@ -234,8 +234,11 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
     T* tokens = e->tokens.as<T>();
     if (mode == MODE_FRAME) {
         ProfScope ps(e, st, CAT_PACK);
-        if (launch_pack_levels<T>(reinterpret_cast<const void* const*>(feats), e->feats_bf16, e->lg, e->cams_embeds.as<float>(),
-                                  e->level_embeds.as<float>(), ncam, C, Nv, tokens, st)) return 2;
+        if (e->feats_bf16 == 2) {
+            if (launch_pack_levels_nhwc<T>(reinterpret_cast<const void* const*>(feats), e->lg, e->cams_embeds.as<float>(),
+                                           e->level_embeds.as<float>(), ncam, C, Nv, tokens, st)) return 2;
+        } else if (launch_pack_levels<T>(reinterpret_cast<const void* const*>(feats), e->feats_bf16, e->lg, e->cams_embeds.as<float>(),
+                                         e->level_embeds.as<float>(), ncam, C, Nv, tokens, st)) return 2;
         e->launches++;
     }
     if constexpr (sizeof(T) == 4) {
@@ -736,7 +739,9 @@ int occb200_engine_finalize(occb200_engine* e)
         if (upload_bf16(e->sca_v_all_wh, W.data(), W.size()) || upload(e->sca_v_all_b, B.data(), B.size())) return 2;
         if (e->sca_value_all.alloc((size_t)c.num_layers * c.num_cams * e->Nv * C * 2 + 256)) return 2;   // (+ one pair over-read)
         OCC_CUDA(cudaMemset(e->sca_value_all.p, 0, e->sca_value_all.bytes));
-        e->value_head_major = getenv("OCC_VALUE_ROWMAJOR") == nullptr;
+        // OCC_VALUE_HEADMAJOR=1: head-major value maps + pair-fetch gathers (sca_pair / tsa_pair).  MEASURED SLOWER than the
+        // row-major layout + sca_pipe / tsa_fused (SCA 1.63 vs 1.32 ms, TSA 0.31 vs 0.23 ms per frame): kept as an experiment
+        e->value_head_major = getenv("OCC_VALUE_HEADMAJOR") != nullptr;
     }
     // decoder: fold BatchNorm3d (eval) into the conv weights; torch layout [Cout][Cin][kz][ky][kx] -> [tap][Cin][Cout]
     for (int i = 0; i < 2; ++i) {
@@ -970,7 +975,7 @@ int occb200_engine_set_prev_rotation(occb200_engine* e, const int32_t* map_host)
 
 int occb200_engine_set_input_dtype(occb200_engine* e, int feats_bf16)
 {
-    OCC_CHECK(e && (feats_bf16 == 0 || feats_bf16 == 1), "input dtype must be 0 (fp32) or 1 (bf16)");
+    OCC_CHECK(e && feats_bf16 >= 0 && feats_bf16 <= 2, "input dtype must be 0 (fp32 NCHW), 1 (bf16 NCHW) or 2 (bf16 NHWC)");
     e->feats_bf16 = feats_bf16;
     return 0;
 }

@@ -53,6 +53,10 @@ struct PackLevels { const void* feat[8]; int hw[8], start[8], tile_begin[8], num
 template <typename T>
 int launch_pack_levels(const void* const* feats, int feats_bf16, const LevelGeom& lg, const float* cams_embeds,
                        const float* level_embeds, int num_cams, int C, int Nv, T* tokens, cudaStream_t stream);
+// same from channels-last bf16 levels [num_cams, h, w, C] (the backbone's native output): an elementwise add, no transpose
+template <typename T>
+int launch_pack_levels_nhwc(const void* const* feats, const LevelGeom& lg, const float* cams_embeds, const float* level_embeds,
+                            int num_cams, int C, int Nv, T* tokens, cudaStream_t stream);
 // y = LayerNorm(x) (eps 1e-5); writes fp32 copy (residual stream), T copy (GEMM operand) and T copy of y + pos
 template <typename T>
 int launch_layernorm(const float* x, const float* gamma, const float* beta, const float* pos, int rows, int C,

@@ -87,13 +87,16 @@ class OccEngine:
         self.Nq = cfg['bev_h'] * cfg['bev_w']
         self.vox_shape = (cfg['bev_w'], cfg['bev_h'], cfg['pillar_h'])
         self._pinned = None
-        self.feat_dtype = torch.float32
+        self.feat_dtype, self.feat_channels_last = torch.float32, False
 
-    def set_input_dtype(self, dtype):
-        """Feature levels are handed over as `dtype` from now on (torch.float32, the reference's, or torch.bfloat16)."""
-        assert dtype in (torch.float32, torch.bfloat16)
-        _lib.check(self.lib.occb200_engine_set_input_dtype(self._h, int(dtype == torch.bfloat16)))
-        self.feat_dtype = dtype
+    def set_input_dtype(self, dtype, channels_last=False):
+        """Feature levels are handed over as `dtype` from now on (torch.float32, the reference's, or torch.bfloat16);
+        `channels_last` (bf16 only): tensors of shape (num_cams, C, h, w) whose MEMORY is (num_cams, h, w, C) -- the
+        backbone engine's native output."""
+        assert dtype in (torch.float32, torch.bfloat16) and not (channels_last and dtype != torch.bfloat16)
+        code = 2 if channels_last else int(dtype == torch.bfloat16)
+        _lib.check(self.lib.occb200_engine_set_input_dtype(self._h, code))
+        self.feat_dtype, self.feat_channels_last = dtype, bool(channels_last)
 
     def __del__(self):
         h = getattr(self, '_h', None)
@@ -123,8 +126,10 @@ class OccEngine:
         for l, (f, (h, w)) in enumerate(zip(feats, self.cfg['level_shapes'])):
             if tuple(f.shape) != (nc, C, h, w):
                 raise ValueError(f'feature level {l}: shape {tuple(f.shape)} != configured {(nc, C, h, w)}')
-            if f.dtype != self.feat_dtype or f.is_cuda != cuda or not f.is_contiguous():
-                raise ValueError(f'feature level {l}: need a contiguous {self.feat_dtype} {"CUDA" if cuda else "CPU (pinned)"} tensor')
+            dense = f.permute(0, 2, 3, 1).is_contiguous() if self.feat_channels_last else f.is_contiguous()
+            if f.dtype != self.feat_dtype or f.is_cuda != cuda or not dense:
+                raise ValueError(f'feature level {l}: need a {"channels-last" if self.feat_channels_last else "contiguous"} '
+                                 f'{self.feat_dtype} {"CUDA" if cuda else "CPU (pinned)"} tensor')
 
     def _feat_ptrs(self, feats):
         arr = (ctypes.c_void_p * 4)()
@@ -137,7 +142,8 @@ class OccEngine:
         C = self.cfg['embed_dims']
         X, Y, Z = self.vox_shape
         dev = self.device
-        feats = [f.contiguous() for f in feats]
+        if not self.feat_channels_last:
+            feats = [f.contiguous() for f in feats]
         self._check_feats(feats, cuda=True)
         out = {}
         if 'bev_embed' in want:

@@ -513,11 +513,13 @@ class BEVFormerOccHead(BaseModule):
                                                               img_shape=img_metas[0]['img_shape'])])
             eng.set_prev_rotation(None if rot_maps is None else rot_maps[b])
             fb = [f[b] for f in mlvl_feats]
-            if fb[0].dtype != eng.feat_dtype:                                 # fp32 (reference dtype) or bf16 features
-                if fb[0].dtype == torch.bfloat16 or eng.feat_dtype == torch.bfloat16:
-                    eng.set_input_dtype(torch.bfloat16 if fb[0].dtype == torch.bfloat16 else torch.float32)
-                if fb[0].dtype != eng.feat_dtype:
-                    fb = [f.float() for f in fb]
+            # fp32 (the reference's dtype), bf16, or bf16 whose memory is channels-last (the native backbone's output)
+            cl = fb[0].dtype == torch.bfloat16 and all((not f.is_contiguous()) and f.permute(0, 2, 3, 1).is_contiguous() for f in fb)
+            want_dt = torch.bfloat16 if fb[0].dtype == torch.bfloat16 else torch.float32
+            if want_dt != eng.feat_dtype or cl != eng.feat_channels_last:
+                eng.set_input_dtype(want_dt, channels_last=cl)
+            if fb[0].dtype != eng.feat_dtype:
+                fb = [f.float() for f in fb]
             out = eng.forward(fb, prev_bev=None if prev_bev is None else prev_bev[b],
                               want=('bev_embed',) if only_bev else want)
             bevs.append(out['bev_embed'])
@@ -605,12 +607,13 @@ class FPN(BaseModule):
 class BEVFormerOcc(BaseModule):
     """reference: detectors/bevformer_occ.py:20-270 (inference shell).  `img_backbone` / `img_neck` are built as
     parameter containers (so reference checkpoints load with their own keys).  Features come from, in this order:
-    `img_feats=` handed to forward / simple_test; a `feature_extractor(img)` callable; or -- opt-in, FIRST VERSION not
-    yet validated on a GPU -- `native_backbone=True`: `occnet_b200.backbone.BackboneEngine`."""
+    `img_feats=` handed to forward / simple_test; a `feature_extractor(img)` callable; or the native ResNet-50 + FPN
+    (`occnet_b200.backbone.BackboneEngine`; `native_backbone=False` turns it off) when the config builds
+    `img_backbone` / `img_neck` -- images then go to voxels without leaving the device (bf16: channels-last hand-over)."""
 
     def __init__(self, pts_bbox_head=None, img_backbone=None, img_neck=None, use_grid_mask=False, video_test_mode=False,
-                 train_cfg=None, test_cfg=None, pretrained=None, feature_extractor=None, native_backbone=False,
-                 backbone_precision='bf16', temporal_test=False, **kwargs):
+                 train_cfg=None, test_cfg=None, pretrained=None, feature_extractor=None, native_backbone=True,
+                 backbone_precision=None, temporal_test=False, **kwargs):
         super().__init__()
         if pts_bbox_head is not None:
             pts_bbox_head = dict(pts_bbox_head)
@@ -622,6 +625,9 @@ class BEVFormerOcc(BaseModule):
         if img_neck is not None and img_neck.get('type') == 'FPN':
             self.img_neck = NECKS.build(dict(img_neck))
         self.feature_extractor = feature_extractor
+        # the backbone runs in the head's precision unless told otherwise (fp32: the reference's arithmetic, CUDA-core GEMMs)
+        if backbone_precision is None:
+            backbone_precision = getattr(self.pts_bbox_head, 'precision', 'fp32')
         self.native_backbone, self.backbone_precision = native_backbone, backbone_precision
         self._backbone_engine, self._backbone_key = None, None
         self.video_test_mode = video_test_mode
@@ -645,7 +651,8 @@ class BEVFormerOcc(BaseModule):
             sd = {k: v for k, v in self.state_dict().items() if k.startswith(('img_backbone.', 'img_neck.'))}
             self._backbone_engine = BackboneEngine(sd, B * N, x.shape[-2:], precision=self.backbone_precision, device=str(x.device))
             self._backbone_key = key
-        feats = self._backbone_engine.forward(x)
+        cl = self.backbone_precision == 'bf16' and getattr(self.pts_bbox_head, 'precision', 'fp32') == 'bf16'
+        feats = self._backbone_engine.forward(x, channels_last_bf16=cl)        # bf16 head: channels-last hand-over, no copies
         if len_queue is not None:
             return [f.view(B // len_queue, len_queue, N, *f.shape[1:]) for f in feats]
         return [f.view(B, N, *f.shape[1:]) for f in feats]
@@ -655,8 +662,8 @@ class BEVFormerOcc(BaseModule):
             return self.feature_extractor(img)
         if self.native_backbone and hasattr(self, 'img_backbone') and hasattr(self, 'img_neck'):
             return self.extract_img_feat(img, img_metas, len_queue=len_queue)
-        raise RuntimeError('BEVFormerOcc: pass img_feats=..., set feature_extractor, or opt in to the (not yet GPU-validated) '
-                           'native ResNet-50 + FPN with native_backbone=True')
+        raise RuntimeError('BEVFormerOcc: pass img_feats=..., set feature_extractor, or configure img_backbone=ResNet / '
+                           'img_neck=FPN with native_backbone=True (the default)')
 
     def obtain_history_bev(self, feats_queue, img_metas_list):
         """reference: detectors/bevformer_occ.py:159-178 -- run the encoder over the history frames (oldest first), each

@@ -17,6 +17,7 @@ pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DEV = 'cuda:0'
+sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))          # tests/golden/sampling.py (shared with gen_fullsize.py)
 
 
 def _oracle():
@@ -525,7 +526,6 @@ def _report(name, vals):
 
 
 def _full6_case(prev=False):
-    sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
     cfg = fixtures.make_cfg('full', num_layers=6)
     params = fixtures.init_params(cfg, seed=2, free_bias=fixtures.FREE_BIAS)
     feats = fixtures.make_feats(cfg, bs=1, seed=100)
@@ -765,7 +765,7 @@ def test_plugin_detector_output_contract():
     from occnet_b200.mmcv_shim import build_detector
     from test_dropin_cpu import head_cfg
     cfg, params, feats, metas, _ = make_case('small6', num_layers=1)
-    det = build_detector(dict(type='BEVFormerOcc', use_grid_mask=True, video_test_mode=True,
+    det = build_detector(dict(type='BEVFormerOcc', use_grid_mask=True, video_test_mode=True, native_backbone=False,
                               img_backbone=dict(type='ResNet', depth=50), img_neck=dict(type='FPN'),
                               pts_bbox_head=head_cfg(cfg))).to(DEV).eval()
     det.pts_bbox_head.load_state_dict(params, strict=True)

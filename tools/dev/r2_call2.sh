@@ -16,7 +16,7 @@ OCC_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_backbone_gpu.py -q -p
 echo "== backbone: $(tail -1 gpurun_out/c2_backbone.log)"
 timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/c2_bench.json 2> gpurun_out/c2_bench.err
 tail -c 600 gpurun_out/c2_bench.json; tail -3 gpurun_out/c2_bench.err
-timeout 1500 python tools/dev/ab.py base= rowmajor=OCC_VALUE_ROWMAJOR:1 tsa_row=OCC_TSA_ROWMAJOR:1 minb5=OCC_SCA_PAIR_MINB:5 \
+timeout 1500 python tools/dev/ab.py base= headmajor=OCC_VALUE_HEADMAJOR:1 \
     nol0=OCC_NO_L0_FOLD:1 conv1lane=OCC_CONV_SINGLE_LANE:1 fp32tc=AB_PRECISION:fp32,AB_TC:1,AB_FRAMES:40 \
     fp32simt=AB_PRECISION:fp32,AB_TC:0,AB_FRAMES:20 > gpurun_out/c2_ab.log 2>&1
 cat gpurun_out/c2_ab.log | cut -c1-400
