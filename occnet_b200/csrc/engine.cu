@@ -401,7 +401,8 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
         }
         const T* sca_val = e->sca_value.as<T>();
         if (hoist_v) {
-            sca_val = reinterpret_cast<const T*>(e->sca_value_all.as<bf16>() + (size_t)l * ncam * Nv * C);
+            static const size_t hack2 = (getenv("OCC_PAIR_HACK") && atoi(getenv("OCC_PAIR_HACK")) == 2) ? 2 : 1;
+            sca_val = reinterpret_cast<const T*>(e->sca_value_all.as<bf16>() + (size_t)l * ncam * Nv * C * hack2);
         } else if (gemm<T, T>(e, tokens, nullptr, 0, w.sca_v_w.as<float>(), w.sca_v_wh.p, w.sca_v_b.as<float>(), nullptr,
                               e->sca_value.as<T>(), ncam * Nv, C, C, ACT_NONE, st)) return 2;
         {
@@ -737,7 +738,8 @@ int occb200_engine_finalize(occb200_engine* e)
             B.insert(B.end(), b->begin(), b->end());
         }
         if (upload_bf16(e->sca_v_all_wh, W.data(), W.size()) || upload(e->sca_v_all_b, B.data(), B.size())) return 2;
-        if (e->sca_value_all.alloc((size_t)c.num_layers * c.num_cams * e->Nv * C * 2 + 256)) return 2;   // (+ one pair over-read)
+        const size_t hack2 = (getenv("OCC_PAIR_HACK") && atoi(getenv("OCC_PAIR_HACK")) == 2) ? 2 : 1;   // timing experiment: 128-byte token pitch
+        if (e->sca_value_all.alloc((size_t)c.num_layers * c.num_cams * e->Nv * C * 2 * hack2 + 256)) return 2;   // (+ one pair over-read)
         OCC_CUDA(cudaMemset(e->sca_value_all.p, 0, e->sca_value_all.bytes));
         // OCC_VALUE_HEADMAJOR=1: head-major value maps + pair-fetch gathers (sca_pair / tsa_pair).  MEASURED SLOWER than the
         // row-major layout + sca_pipe / tsa_fused (SCA 1.63 vs 1.32 ms, TSA 0.31 vs 0.23 ms per frame): kept as an experiment

@@ -208,8 +208,14 @@ __device__ __forceinline__ void shuffle_gather(Acc<T>& acc, const T* __restrict_
 //            4*DEPTH independent loads in flight -- the previous version waited on each sample's loads (ncu: 5.5 of 10
 //            stall cycles per issue were long-scoreboard) because the validity branch fenced the loads.
 // geom(i, base, W): value pointer (already offset to this lane's head / channel slice) and row pitch of sample i.
+// Descriptor slot of (sample i, head): i*8 + (head ^ 2*(i & 3)).  The XOR makes the WRITER conflict-free: the 8 lanes of a
+// quarter-warp are (heads 2k, 2k+1) x (levels s = 0..3) and write rows i = 4p + s that are 128 B apart (same banks) -- with the
+// plain [sample][head] order that was a 4-way bank conflict (ncu: 16 wavefronts per STS.128 instead of 4, 13 % of the kernel's L1
+// data-pipe wavefronts); the reader still sees 8 distinct 16-byte groups of one 128-byte row.
+__device__ __forceinline__ int desc_slot(int i, int head) { return i * 8 + (head ^ (2 * (i & 3))); }
+
 template <int NS, int DEPTH, typename Geom>
-__device__ __forceinline__ void gather_descs(float (&acc)[8], const uint4* dsm, Geom geom)
+__device__ __forceinline__ void gather_descs(float (&acc)[8], const uint4* dsm, int head, Geom geom)
 {
     uint4 d[DEPTH + 1];
     uint4 v[DEPTH + 1][4];
@@ -217,7 +223,7 @@ __device__ __forceinline__ void gather_descs(float (&acc)[8], const uint4* dsm, 
     for (int i = 0; i < NS + DEPTH; ++i) {
         if (i < NS) {
             const int slot = i % (DEPTH + 1);
-            d[slot] = dsm[i * 8];
+            d[slot] = dsm[desc_slot(i, head)];
             const bf16* base; int W;
             geom(i, base, W);
             if (d[slot].x & CODE_VALID) {
@@ -355,13 +361,13 @@ sca_pipe_kernel(const bf16* __restrict__ value, const QT* __restrict__ qproj, Sc
                 // (u + dx/W) * W - 0.5 == u*W + dx - 0.5 up to fp32 rounding (bf16 path: not bit-matched to the fp32 one)
                 const float w_im = fmaf(u, own_w, off[2 * p] - 0.5f);
                 const float h_im = fmaf(v, own_h, off[2 * p + 1] - 0.5f);
-                dw[(p * 4 + s) * 8 + head] = make_desc(prep_sample(h_im, w_im, wl[p] * inv, own_H, own_W, own_start));
+                dw[desc_slot(p * 4 + s, head)] = make_desc(prep_sample(h_im, w_im, wl[p] * inv, own_H, own_W, own_start));
             }
         }
         __syncwarp();
         // ---- phase 2
         const bf16* vcam = value + ((int64_t)c * Nv * 8 + head) * 32 + s * 8;
-        gather_descs<32, DEPTH>(acc, dw + head, [&](int i, const bf16*& base, int& W) { base = vcam; W = lg.w[i & 3]; });
+        gather_descs<32, DEPTH>(acc, dw, head, [&](int i, const bf16*& base, int& W) { base = vcam; W = lg.w[i & 3]; });
         __syncwarp();
     }
     const float scale = (float)max(count, 1);
@@ -381,22 +387,28 @@ sca_pipe_kernel(const bf16* __restrict__ value, const QT* __restrict__ qproj, Sc
 //   Lane map in phase 2: hl = lane / 8 (head within the group of 4), j = lane % 8: side = j / 4 (left / right pixel),
 //   slice = j % 4 (8 channels).  Two head groups -> 2 x 8 accumulators per lane; left and right partial sums are combined
 //   with one shuffle per accumulator at the end.  Phase 1 (descriptors) is the row-major kernel's.
+// hack (timing experiments only, results are garbage): 1 = every pair forced onto an even token (line-aligned fetches with
+// the real footprint), 2 = token pitch 128 B (line-aligned fetches with the footprint of a duplicated-pair layout)
 template <int NS, int DEPTH, typename Geom>
-__device__ __forceinline__ void gather_descs_pair(float (&acc)[8], const uint4* dsm, int side, Geom geom)
+__device__ __forceinline__ void gather_descs_pair(float (&acc)[8], const uint4* dsm, int head, int side, Geom geom, int hack = 0,
+                                                  int64_t tok0 = 0)
 {
     uint4 d[DEPTH + 1];
     uint4 v[DEPTH + 1][2];
+    const int pitch = hack == 2 ? 64 : 32;
 #pragma unroll
     for (int i = 0; i < NS + DEPTH; ++i) {
         if (i < NS) {
             const int slot = i % (DEPTH + 1);
-            d[slot] = dsm[i * 8];
+            d[slot] = dsm[desc_slot(i, head)];
             const bf16* base; int W;
             geom(i, base, W);
             if (d[slot].x & CODE_VALID) {
-                const bf16* p = base + (int64_t)(d[slot].x & CODE_OFF_MASK) * 32;
+                int64_t tok = tok0 + (int64_t)(d[slot].x & CODE_OFF_MASK);
+                if (hack == 1) tok &= ~(int64_t)1;
+                const bf16* p = base + tok * pitch;
                 v[slot][0] = __ldg(reinterpret_cast<const uint4*>(p));
-                v[slot][1] = __ldg(reinterpret_cast<const uint4*>(p + (int64_t)W * 32));
+                v[slot][1] = __ldg(reinterpret_cast<const uint4*>(p + (int64_t)W * pitch));
             }
         }
         if (i >= DEPTH) {
@@ -413,7 +425,7 @@ __device__ __forceinline__ void gather_descs_pair(float (&acc)[8], const uint4* 
 template <typename QT, int DEPTH, int MINB, int NW>
 __global__ void __launch_bounds__(NW * 32, MINB)
 sca_pair_kernel(const bf16* __restrict__ value_hm, const QT* __restrict__ qproj, ScaParams sp, LevelGeom lg, int Nv,
-                long long T, bf16* __restrict__ out, uint8_t* __restrict__ hits)
+                long long T, bf16* __restrict__ out, uint8_t* __restrict__ hits, int hack)
 {
     __shared__ uint4 descs[NW][32 * 8];                          // [warp][sample = point*4 + level][head]
     const int Nq = sp.bev_h * sp.bev_w;
@@ -475,15 +487,17 @@ sca_pair_kernel(const bf16* __restrict__ value_hm, const QT* __restrict__ qproj,
                 const float v = __shfl_sync(FULL, r ? rv[1] : rv[0], asrc);
                 const float w_im = fmaf(u, own_w, off[2 * p] - 0.5f);
                 const float h_im = fmaf(v, own_h, off[2 * p + 1] - 0.5f);
-                dw[(p * 4 + s) * 8 + head] = make_desc(prep_sample(h_im, w_im, wl[p] * inv, own_H, own_W, own_start));
+                dw[desc_slot(p * 4 + s, head)] = make_desc(prep_sample(h_im, w_im, wl[p] * inv, own_H, own_W, own_start));
             }
         }
         __syncwarp();
         // value_hm + (head * T + cam * Nv) * 32 + j * 8: lanes j = 0..7 of a head read 128 contiguous bytes
-        const bf16* v0 = value_hm + ((int64_t)hl * T + (int64_t)c * Nv) * 32 + j * 8;
-        const bf16* v1 = v0 + 4 * T * 32;
-        gather_descs_pair<32, DEPTH>(acc0, dw + hl, side, [&](int i, const bf16*& base, int& W) { base = v0; W = lg.w[i & 3]; });
-        gather_descs_pair<32, DEPTH>(acc1, dw + 4 + hl, side, [&](int i, const bf16*& base, int& W) { base = v1; W = lg.w[i & 3]; });
+        const int64_t hstride = T * (hack == 2 ? 64 : 32);               // elements per head plane
+        const bf16* v0 = value_hm + (int64_t)hl * hstride + j * 8;
+        const bf16* v1 = v0 + 4 * hstride;
+        const int64_t tok0 = (int64_t)c * Nv;
+        gather_descs_pair<32, DEPTH>(acc0, dw, hl, side, [&](int i, const bf16*& base, int& W) { base = v0; W = lg.w[i & 3]; }, hack, tok0);
+        gather_descs_pair<32, DEPTH>(acc1, dw, 4 + hl, side, [&](int i, const bf16*& base, int& W) { base = v1; W = lg.w[i & 3]; }, hack, tok0);
         __syncwarp();
     }
     const float scale = (float)max(count, 1);
@@ -641,8 +655,8 @@ tsa_pair_kernel(const bf16* __restrict__ value_prev_hm, const bf16* __restrict__
     const float wim1 = __fadd_rn(rx, __fdiv_rn(offv[2], fw)) * fw - 0.5f;
     const float him1 = __fadd_rn(ry, __fdiv_rn(offv[3], fh)) * fh - 0.5f;
     uint4* dw = descs[threadIdx.x >> 5];
-    dw[(qu_own * 4 + p0) * 8 + head] = make_desc(prep_sample(him0, wim0, wt0, bev_h, bev_w));
-    dw[(qu_own * 4 + p0 + 1) * 8 + head] = make_desc(prep_sample(him1, wim1, wt1, bev_h, bev_w));
+    dw[desc_slot(qu_own * 4 + p0, head)] = make_desc(prep_sample(him0, wim0, wt0, bev_h, bev_w));
+    dw[desc_slot(qu_own * 4 + p0 + 1, head)] = make_desc(prep_sample(him1, wim1, wt1, bev_h, bev_w));
     __syncwarp();
     float acc0[8], acc1[8];
 #pragma unroll
@@ -650,8 +664,8 @@ tsa_pair_kernel(const bf16* __restrict__ value_prev_hm, const bf16* __restrict__
     const int64_t plane = (int64_t)Nq * 32;
     const bf16* p0v = value_prev_hm + (int64_t)hl * plane + j * 8;
     const bf16* c0v = value_cur_hm + (int64_t)hl * plane + j * 8;
-    gather_descs_pair<8, 2>(acc0, dw + hl, side, [&](int i, const bf16*& base, int& W) { base = i < 4 ? p0v : c0v; W = bev_w; });
-    gather_descs_pair<8, 2>(acc1, dw + 4 + hl, side,
+    gather_descs_pair<8, 2>(acc0, dw, hl, side, [&](int i, const bf16*& base, int& W) { base = i < 4 ? p0v : c0v; W = bev_w; });
+    gather_descs_pair<8, 2>(acc1, dw, 4 + hl, side,
                             [&](int i, const bf16*& base, int& W) { base = (i < 4 ? p0v : c0v) + 4 * plane; W = bev_w; });
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -892,11 +906,12 @@ int launch_sca_pair(const bf16* value_hm, const void* qproj_v, bool q_half, cons
     // 6 CTAs/SM caps the kernel at 80 registers (a few spills outside the gather loop); OCC_SCA_PAIR_MINB=5 trades occupancy
     // for none (measured variants: profiles/README.md)
     static const int minb = getenv("OCC_SCA_PAIR_MINB") ? atoi(getenv("OCC_SCA_PAIR_MINB")) : 6;
+    static const int hack = getenv("OCC_PAIR_HACK") ? atoi(getenv("OCC_PAIR_HACK")) : 0;     // timing experiments only
     if (q_half) {
-        if (minb == 5) sca_pair_kernel<__half, 1, 5, 4><<<ceil_div(Nq, 4), 128, 0, stream>>>(value_hm, (const __half*)qproj_v, sp, lg, Nv, T, out, hits);
-        else           sca_pair_kernel<__half, 1, 6, 4><<<ceil_div(Nq, 4), 128, 0, stream>>>(value_hm, (const __half*)qproj_v, sp, lg, Nv, T, out, hits);
+        if (minb == 5) sca_pair_kernel<__half, 1, 5, 4><<<ceil_div(Nq, 4), 128, 0, stream>>>(value_hm, (const __half*)qproj_v, sp, lg, Nv, T, out, hits, hack);
+        else           sca_pair_kernel<__half, 1, 6, 4><<<ceil_div(Nq, 4), 128, 0, stream>>>(value_hm, (const __half*)qproj_v, sp, lg, Nv, T, out, hits, hack);
     } else {
-        sca_pair_kernel<float, 1, 6, 4><<<ceil_div(Nq, 4), 128, 0, stream>>>(value_hm, (const float*)qproj_v, sp, lg, Nv, T, out, hits);
+        sca_pair_kernel<float, 1, 6, 4><<<ceil_div(Nq, 4), 128, 0, stream>>>(value_hm, (const float*)qproj_v, sp, lg, Nv, T, out, hits, hack);
     }
     OCC_CUDA(cudaGetLastError());
     return 0;

@@ -28,9 +28,14 @@ LAUNCHES_PER_FRAME = {'sca_gather': 6, 'tsa_gather': 6, 'conv3d': 2, 'occ_head':
 
 
 def rows_of(rep):
-    out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    """Per-launch rows of an .ncu-rep, or of a `ncu -i X.ncu-rep --page raw --csv` export made on the GPU box (*.csv)."""
+    if rep.endswith('.csv'):
+        out = open(rep).read()
+    else:
+        out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     r = list(csv.reader(io.StringIO(out)))
     hdr, units = r[0], r[1]
+    hdr = [h.split('.TriageCompute.')[-1] if '.TriageCompute.' in h else h for h in hdr]
     for row in r[2:]:
         d = {'kernel': re.sub(r'\(.*', '', row[hdr.index('Kernel Name')]).replace('void occ::<unnamed>::', '')}
         for k in KEYS:
@@ -43,8 +48,9 @@ def rows_of(rep):
         yield d
 
 
-def traffic_of(rows, source):
-    """DRAM bytes per launch / per frame by kernel category from the per-launch rows."""
+def traffic_of(rows, source, whole_frame=False):
+    """DRAM bytes per launch / per frame by kernel category from the per-launch rows.  whole_frame: the rows are exactly
+    one frame (every launch captured once), so per-frame numbers are plain sums."""
     traffic = {}
     for pat, cat in CATEGORY:
         sel = [d for d in rows if pat in d['kernel']]
@@ -54,6 +60,9 @@ def traffic_of(rows, source):
         dur = [float(d['gpu__time_duration.sum']) for d in sel]
         traffic[cat] = {'dram_bytes_per_launch': sum(per) / len(per), 'captured_launches': len(sel),
                         'avg_duration_us': sum(dur) / len(dur), 'source': source}
+        if whole_frame:
+            traffic[cat].update(dram_bytes_per_frame=sum(per), launches_per_frame=len(sel), duration_us_per_frame=sum(dur))
+            continue
         if cat in LAUNCHES_PER_FRAME:
             traffic[cat]['dram_bytes_per_frame'] = traffic[cat]['dram_bytes_per_launch'] * LAUNCHES_PER_FRAME[cat]
         if cat == 'gemm' and len(sel) >= 8:
@@ -76,14 +85,17 @@ def main(reps):
         for k, v in traffic.items():
             print(k, {a: (round(b / 1e6, 1) if 'bytes' in a else b) for a, b in v.items() if a not in ('source', 'note')})
         return
+    tag, whole = 'r1', False
+    if reps and reps[0] == '--frame':                           # --frame TAG file: one whole frame captured (57 launches)
+        tag, whole, reps = reps[1], True, reps[2:]
     rows = [d for rep in reps for d in rows_of(rep)]
-    with open(os.path.join(HERE, 'r1_ncu_summary.csv'), 'w', newline='') as f:
+    with open(os.path.join(HERE, tag + '_ncu_summary.csv'), 'w', newline='') as f:
         w = csv.writer(f)
         w.writerow(['kernel'] + KEYS)
         for d in rows:
             w.writerow([d['kernel']] + [d.get(k, '') for k in KEYS])
-    traffic = traffic_of(rows, ', '.join(os.path.basename(r) for r in reps))
-    json.dump(traffic, open(os.path.join(HERE, 'r1_traffic.json'), 'w'), indent=1)
+    traffic = traffic_of(rows, ', '.join(os.path.basename(r) for r in reps), whole)
+    json.dump(traffic, open(os.path.join(HERE, tag + '_traffic.json'), 'w'), indent=1)
     for k, v in traffic.items():
         print(k, {a: (round(b / 1e6, 1) if 'bytes' in a else b) for a, b in v.items() if a not in ('source', 'note')})
 
