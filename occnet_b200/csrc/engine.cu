@@ -66,6 +66,7 @@ struct occb200_engine {
     ScaParams sp;
     bool cameras_set = false, finalized = false, taps = false;
     bool value_head_major = false;      // SCA value maps as [layer][head][token][32] (pair-fetch gather) instead of [layer][token][256]
+    DevBuf sca_sched;                   // scheduler words of the SM-tiled gather kernel (zeroed by every launch)
     DevBuf rot_map;                     // occb200_engine_set_prev_rotation: source row of every BEV cell (int32, -1 = outside)
     bool rot_set = false;
     int feats_bf16 = 0;                 // occb200_engine_set_input_dtype: feature levels arrive as bf16 instead of fp32
@@ -410,7 +411,8 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
             if (hoist_v && e->value_head_major) {
                 if (launch_sca_pair(reinterpret_cast<const bf16*>(sca_val), qproj, q_half, e->sp, e->lg, Nv,
                                     reinterpret_cast<bf16*>(attn_out), e->hits.as<uint8_t>(), st)) return 2;
-            } else if (launch_sca_fused<T>(sca_val, qproj, q_half, e->sp, e->lg, Nv, attn_out, e->hits.as<uint8_t>(), st)) return 2;
+            } else if (launch_sca_fused<T>(sca_val, qproj, q_half, e->sp, e->lg, Nv, attn_out, e->hits.as<uint8_t>(), st,
+                                           e->sca_sched.as<unsigned>())) return 2;
         }
         e->launches++;
         if (fuse_ln) {
@@ -582,7 +584,7 @@ void occb200_engine_destroy(occb200_engine* e)
                          &w.tsa_q_wh_fold, &w.tsa_q_const};
         for (DevBuf* b : all) b->release();
     }
-    DevBuf* all[] = {&e->rot_map, &e->split_ws, &e->tokens_split, &e->l0_x_f32, &e->l0_q_t, &e->pos_bf, &e->qc_f32, &e->qc_t, &e->qc_pos_t, &e->bev_queries, &e->pos, &e->pos_t32, &e->cams_embeds, &e->level_embeds, &e->conv_w[0], &e->conv_w[1],
+    DevBuf* all[] = {&e->sca_sched, &e->rot_map, &e->split_ws, &e->tokens_split, &e->l0_x_f32, &e->l0_q_t, &e->pos_bf, &e->qc_f32, &e->qc_t, &e->qc_pos_t, &e->bev_queries, &e->pos, &e->pos_t32, &e->cams_embeds, &e->level_embeds, &e->conv_w[0], &e->conv_w[1],
                      &e->conv_b[0], &e->conv_b[1], &e->conv_wh[0], &e->conv_wh[1], &e->sca_v_all_wh, &e->sca_v_all_b, &e->sca_value_all, &e->hw1, &e->hb1, &e->hw2, &e->hb2,
                      &e->fw1, &e->fb1, &e->fw2, &e->fb2, &e->head_w1h, &e->head_w2h, &e->head_b1c, &e->head_b2c, &e->tokens, &e->sca_value, &e->q_f32, &e->q_t,
                      &e->q_pos_t, &e->q0_t, &e->prev_t, &e->tsa_value, &e->tsa_value_prev, &e->qproj, &e->attn_out,
@@ -812,7 +814,7 @@ int occb200_engine_finalize(occb200_engine* e)
         e->tsa_value_prev.alloc((size_t)Nq * C * es) || e->qproj.alloc((size_t)Nq * maxq * 4) ||
         e->attn_out.alloc((size_t)Nq * C * es) || e->x_f32.alloc(nq_pad * C * 4) ||
         e->ffn_h.alloc((size_t)Nq * F * es) || e->vox0.alloc(nvox * mid * es) || e->vox1.alloc(nvox * od * es) ||
-        e->vox2.alloc(nvox * od * es) || e->hits.alloc(Nq)) return 2;
+        e->vox2.alloc(nvox * od * es) || e->hits.alloc(Nq) || e->sca_sched.alloc(SCA_SCHED_WORDS * sizeof(unsigned))) return 2;
     OCC_CUDA(cudaMemset(e->q_f32.p, 0, nq_pad * C * 4));
     OCC_CUDA(cudaMemset(e->x_f32.p, 0, nq_pad * C * 4));
     if (tc32) {

@@ -294,20 +294,19 @@ __device__ __forceinline__ uint4 make_desc(const SamplePrep& sm)
     return make_uint4((uint32_t)sm.code, pack_bf16x2(sm.c1, sm.c2), pack_bf16x2(sm.c3, sm.c4), 0u);
 }
 
-template <typename QT, int DEPTH, int MINB, int NW>
-__global__ void __launch_bounds__(NW * 32, MINB)
-sca_pipe_kernel(const bf16* __restrict__ value, const QT* __restrict__ qproj, ScaParams sp, LevelGeom lg,
-                int Nv, bf16* __restrict__ out, uint8_t* __restrict__ hits)
+// one BEV query per warp (the body of both production kernels below); dw = this warp's 4 KB descriptor block
+// getq() returns the query index: the body is register-tight (80 = 6 CTAs/SM) and must be able to RE-DERIVE q where it is used
+// (linear kernel: from blockIdx; SM-tiled kernel: re-read from shared memory) instead of keeping it live across the gather.
+template <typename QT, int DEPTH, typename GetQ>
+__device__ __forceinline__ void sca_pipe_query(GetQ getq, const bf16* __restrict__ value, const QT* __restrict__ qproj,
+                                               const ScaParams& sp, const LevelGeom& lg, int Nv, bf16* __restrict__ out,
+                                               uint8_t* __restrict__ hits, uint4* dw)
 {
-    __shared__ uint4 descs[NW][32 * 8];                          // [warp][sample = point*4 + level][head]
-    const int Nq = sp.bev_h * sp.bev_w;
-    const int q = blockIdx.x * NW + (threadIdx.x >> 5);
-    if (q >= Nq) return;
     const int lane = threadIdx.x & 31, head = lane >> 2, s = lane & 3;   // s doubles as the owned level
     const unsigned FULL = 0xffffffffu;
 
-    const float xs = __fdiv_rn((float)(q % sp.bev_w) + 0.5f, (float)sp.bev_w);
-    const float ys = __fdiv_rn((float)(q / sp.bev_w) + 0.5f, (float)sp.bev_h);
+    const float xs = __fdiv_rn((float)(getq() % sp.bev_w) + 0.5f, (float)sp.bev_w);
+    const float ys = __fdiv_rn((float)(getq() / sp.bev_w) + 0.5f, (float)sp.bev_h);
     float ru[2], rv[2];
     unsigned vis = 0;
 #pragma unroll
@@ -321,12 +320,11 @@ sca_pipe_kernel(const bf16* __restrict__ value, const QT* __restrict__ qproj, Sc
         for (int k = 0; k < 4; ++k) if ((b >> (8 * k)) & 0xffu) vis |= 1u << (r * 4 + k);
     }
     const int count = __popc(vis);
-    if (hits && lane == 0) hits[q] = (uint8_t)count;
+    if (hits && lane == 0) hits[getq()] = (uint8_t)count;
 
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    uint4* dw = descs[threadIdx.x >> 5];
     const int own_W = s == 0 ? lg.w[0] : s == 1 ? lg.w[1] : s == 2 ? lg.w[2] : lg.w[3];
     const int own_H = s == 0 ? lg.h[0] : s == 1 ? lg.h[1] : s == 2 ? lg.h[2] : lg.h[3];
     const int own_start = s == 0 ? lg.start[0] : s == 1 ? lg.start[1] : s == 2 ? lg.start[2] : lg.start[3];
@@ -337,7 +335,7 @@ sca_pipe_kernel(const bf16* __restrict__ value, const QT* __restrict__ qproj, Sc
         // ---- phase 1: my (head, level s): 8 offsets + 8 logits -> 8 descriptors.  (Reloaded per visible camera --
         // 1.2 on average -- so that nothing but the accumulators stays live across the gather.)
         {
-            const QT* qp = qproj + (int64_t)q * 768;
+            const QT* qp = qproj + (int64_t)getq() * 768;
             float off[16], wl[8];
             load_q<16>(qp + head * 64 + s * 16, off);
             load_q<8>(qp + 512 + head * 32 + s * 8, wl);
@@ -373,7 +371,89 @@ sca_pipe_kernel(const bf16* __restrict__ value, const QT* __restrict__ qproj, Sc
     const float scale = (float)max(count, 1);
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = __fdiv_rn(acc[i], scale);
-    store8(out + (int64_t)q * 256 + head * 32 + s * 8, acc);
+    store8(out + (int64_t)getq() * 256 + head * 32 + s * 8, acc);
+}
+
+// Linear mapping: CTA b = queries [b*NW, (b+1)*NW) in BEV raster order (kept as the A/B reference: OCC_SCA_TILED=0).
+template <typename QT, int DEPTH, int MINB, int NW>
+__global__ void __launch_bounds__(NW * 32, MINB)
+sca_pipe_kernel(const bf16* __restrict__ value, const QT* __restrict__ qproj, ScaParams sp, LevelGeom lg,
+                int Nv, bf16* __restrict__ out, uint8_t* __restrict__ hits)
+{
+    __shared__ uint4 descs[NW][32 * 8];                          // [warp][sample = point*4 + level][head ^ swizzle]
+    auto getq = [] { return (int)(blockIdx.x * NW + (threadIdx.x >> 5)); };
+    if (getq() >= sp.bev_h * sp.bev_w) return;
+    sca_pipe_query<QT, DEPTH>(getq, value, qproj, sp, lg, Nv, out, hits, descs[threadIdx.x >> 5]);
+}
+
+// ------------------------------------------------------------------------------------------
+// SM-tiled persistent variant (EXPERIMENT, off by default: measured slower, see launch_sca_fused).  Hypothesis: the gather is
+// bound by L2 -> L1 traffic (ncu, linear mapping: 1.48 GB per launch over the crossbar at 6.5 TB/s, L1 hit rate 47 %, DRAM 8 %):
+// neighbouring BEV queries project onto overlapping image regions, but consecutive CTAs of a linear grid land on DIFFERENT SMs,
+// so the 24 warps resident on an SM work on 6 unrelated strips.
+// Here every SM works on ONE compact BEV tile (TW x TH = 8 x 3 queries = 6 units of 4 x-consecutive queries) at a time:
+//   * grid = #SMs x MINB persistent CTAs of 4 warps; a CTA reads %smid and takes the next unit of its SM's current tile from
+//     one 32-bit word per SM:  word = (tile + 1) << 16 | c;  old = atomicAdd(word, 1), c = old & 0xffff:
+//        tile set, c in [2, U]            -> unit c - 1 of that tile
+//        (no tile, c == 0) or c == U + 1  -> this CTA fetches the SM's next tile t = atomicAdd(global, 1), takes its unit 0 and
+//                                            publishes word = (t + 1) << 16 | 2  (t >= number of tiles: word = DONE)
+//        otherwise                        -> another CTA of this SM is fetching: retry
+//     All-zero words (one cudaMemsetAsync per launch) are the initial state.  Balance is dynamic at tile granularity and no
+//     assumption is made about which / how many CTAs the hardware places on an SM.
+//   * tools/dev/sca_l1_sim.py (LRU model of the bench geometry): L2 -> L1 bytes 1.16 GB -> 0.5-0.6 GB per launch.
+constexpr int SCA_TILE_W = 8, SCA_TILE_H = 3, SCA_TILE_UNITS = (SCA_TILE_W / 4) * SCA_TILE_H;
+constexpr unsigned SCA_TILE_DONE = 0xffffu;
+
+// next unit of this SM's current tile -> first query of the unit (4 x-consecutive queries), -1 = all tiles done, -2 = the unit
+// lies outside the BEV grid.  Kept out of line: nothing of the scheduler stays live across the (register-tight) query body.
+__device__ __noinline__ int sca_tile_next(unsigned* __restrict__ sched, int sched_global, int bev_w, int bev_h)
+{
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    unsigned* word = sched + min(smid, (unsigned)sched_global - 1);
+    const int tiles_x = (bev_w + SCA_TILE_W - 1) / SCA_TILE_W, tiles_y = (bev_h + SCA_TILE_H - 1) / SCA_TILE_H;
+    const unsigned num_tiles = (unsigned)(tiles_x * tiles_y);
+    unsigned tile, unit;
+    for (;;) {
+        const unsigned old = atomicAdd(word, 1u);
+        const unsigned tf = old >> 16, c = old & 0xffffu;            // tf = current tile + 1 (0: none yet)
+        if (tf == SCA_TILE_DONE) return -1;
+        if (tf != 0 && c >= 2 && c <= (unsigned)SCA_TILE_UNITS) { tile = tf - 1; unit = c - 1; break; }
+        if (tf == 0 ? c == 0 : c == (unsigned)SCA_TILE_UNITS + 1) {
+            const unsigned t = atomicAdd(sched + sched_global, 1u);
+            if (t >= num_tiles) { atomicExch(word, (SCA_TILE_DONE << 16) | 8u); return -1; }
+            atomicExch(word, ((t + 1) << 16) | 2u);
+            tile = t; unit = 0;
+            break;
+        }
+        __nanosleep(64);                                             // another CTA of this SM is publishing the next tile
+    }
+    const int x = (int)(tile % tiles_x) * SCA_TILE_W + (int)(unit % (SCA_TILE_W / 4)) * 4;
+    const int y = (int)(tile / tiles_x) * SCA_TILE_H + (int)(unit / (SCA_TILE_W / 4));
+    return (y < bev_h && x < bev_w) ? y * bev_w + x : -2;
+}
+
+template <typename QT, int DEPTH, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+sca_tile_kernel(const bf16* __restrict__ value, const QT* __restrict__ qproj, ScaParams sp, LevelGeom lg,
+                int Nv, bf16* __restrict__ out, uint8_t* __restrict__ hits, unsigned* __restrict__ sched /* [max smid + 1] + global */,
+                int sched_global)
+{
+    __shared__ uint4 descs[4][32 * 8];
+    __shared__ int s_q[2];                                       // double-buffered: one __syncthreads per unit
+    int it = 0;
+    if (threadIdx.x == 0) s_q[0] = sca_tile_next(sched, sched_global, sp.bev_w, sp.bev_h);
+    for (;; it ^= 1) {
+        __syncthreads();
+        const int q0 = s_q[it];
+        if (q0 == -1) return;
+        // the unit after this one is fetched now (atomic round trip hidden behind this unit's gather)
+        if (threadIdx.x == 0) s_q[it ^ 1] = sca_tile_next(sched, sched_global, sp.bev_w, sp.bev_h);
+        const volatile int* sq = &s_q[it];
+        auto getq = [sq] { return *sq + (int)(threadIdx.x >> 5); };   // re-read, not kept live (see sca_pipe_query)
+        if (q0 >= 0)                                                 // (bev_w % 4 == 0: a unit of 4 queries never wraps a row)
+            sca_pipe_query<QT, DEPTH>(getq, value, qproj, sp, lg, Nv, out, hits, descs[threadIdx.x >> 5]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -846,9 +926,18 @@ int launch_tsa_fused(const T* value_prev, const T* value_cur, const void* qproj,
 template int launch_tsa_fused<float>(const float*, const float*, const void*, bool, int, int, float*, cudaStream_t);
 template int launch_tsa_fused<bf16>(const bf16*, const bf16*, const void*, bool, int, int, bf16*, cudaStream_t);
 
+static int num_sms_here()                                            // per device: one process may drive several GPUs
+{
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cache[dev] == 0) cudaDeviceGetAttribute(&cache[dev], cudaDevAttrMultiProcessorCount, dev);
+    return cache[dev] > 0 ? cache[dev] : 148;
+}
+
 template <typename T>
 int launch_sca_fused(const T* value, const void* qproj_v, bool q_half, const ScaParams& sp, const LevelGeom& lg, int Nv,
-                     T* out, uint8_t* hits, cudaStream_t stream)
+                     T* out, uint8_t* hits, cudaStream_t stream, unsigned* sched)
 {
     OCC_CHECK(lg.num_levels == 4 && sp.num_cams <= 8 && sp.D <= 8 && sp.D >= 1 && 8 % sp.D == 0,
               "sca_fused: supports 4 levels, <= 8 cameras, pillar anchors in {1,2,4,8}");
@@ -859,6 +948,25 @@ int launch_sca_fused(const T* value, const void* qproj_v, bool q_half, const Sca
         // production bf16 kernel: descriptor-staged gather, 4 warps per CTA, 6 CTAs per SM (OCC_SCA_PIPE=0: the
         // shuffle-broadcast kernel that is also the fp32 path; measured variants: profiles/README.md)
         static const int pipe = getenv("OCC_SCA_PIPE") ? atoi(getenv("OCC_SCA_PIPE")) : 416;
+        // OCC_SCA_TILED=6|5: the SM-tiled persistent kernel (6 / 5 CTAs per SM).  MEASURED SLOWER than the linear mapping although it
+        // does what it was built for (ncu, r2 calls 5-6: L1 hit rate 47 -> 64 %, L2->L1 bytes 1.48 -> 1.03 GB, shared-memory
+        // wavefronts -44 %): 268-282 us vs 225 us per launch -- the gather is not bound by L2->L1 bytes (profiles/README.md).
+        static const int tiled = getenv("OCC_SCA_TILED") ? atoi(getenv("OCC_SCA_TILED")) : 0;
+        if (tiled && sched != nullptr && sp.bev_w % 4 == 0) {
+            // SM-tiled persistent kernel: one word per SM (indexed by %smid, < SCA_SCHED_WORDS - 1) + the global tile counter
+            OCC_CUDA(cudaMemsetAsync(sched, 0, SCA_SCHED_WORDS * sizeof(unsigned), stream));
+            // tiled = 6: 6 CTAs/SM (80 registers, ~40 spilled words per query); 5: 5 CTAs/SM (96 registers, none)
+            const int per_sm = tiled == 5 ? 5 : 6;
+            const int grid = num_sms_here() * per_sm;
+            if (q_half) {
+                if (per_sm == 5) sca_tile_kernel<__half, 1, 5><<<grid, 128, 0, stream>>>(value, (const __half*)qproj_v, sp, lg, Nv, out, hits, sched, SCA_SCHED_WORDS - 1);
+                else             sca_tile_kernel<__half, 1, 6><<<grid, 128, 0, stream>>>(value, (const __half*)qproj_v, sp, lg, Nv, out, hits, sched, SCA_SCHED_WORDS - 1);
+            } else {
+                sca_tile_kernel<float, 1, 6><<<grid, 128, 0, stream>>>(value, (const float*)qproj_v, sp, lg, Nv, out, hits, sched, SCA_SCHED_WORDS - 1);
+            }
+            OCC_CUDA(cudaGetLastError());
+            return 0;
+        }
         bool done = true;
 #define OCC_SCA_CASE(W, D, B)                                                                                       \
     case 100 * W + 10 * D + B:                                                                                      \
@@ -880,9 +988,9 @@ int launch_sca_fused(const T* value, const void* qproj_v, bool q_half, const Sca
     return 0;
 }
 template int launch_sca_fused<float>(const float*, const void*, bool, const ScaParams&, const LevelGeom&, int, float*,
-                                     uint8_t*, cudaStream_t);
+                                     uint8_t*, cudaStream_t, unsigned*);
 template int launch_sca_fused<bf16>(const bf16*, const void*, bool, const ScaParams&, const LevelGeom&, int, bf16*,
-                                    uint8_t*, cudaStream_t);
+                                    uint8_t*, cudaStream_t, unsigned*);
 
 int launch_tsa_pair(const bf16* value_prev_hm, const bf16* value_cur_hm, const void* qproj, bool q_half, int bev_h, int bev_w,
                     bf16* out, cudaStream_t stream)
