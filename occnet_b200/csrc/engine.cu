@@ -345,9 +345,30 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
             return gemm<T, T>(e, a, nullptr, 0, w.tsa_v_w.as<float>(), w.tsa_v_wh.p, w.tsa_v_b.as<float>(), nullptr, dst, Nq, C, C,
                               ACT_NONE, st);
         };
+        // value_proj of every queue entry + the sampling projection are independent GEMMs over [Nq,256] operands: ONE launch on
+        // disjoint CTA ranges (OCC_TSA_MERGE=0: one launch each)
+        static const bool tsa_merge_env = getenv("OCC_TSA_MERGE") == nullptr || atoi(getenv("OCC_TSA_MERGE")) != 0;
+        const bool tsa_merge = sizeof(T) == 2 && fuse_ln && q_half && !tsa_hm && tsa_merge_env && w.tsa_v_wh.p != nullptr;
+        if (has_prev) v_prev = e->tsa_value_prev.as<T>();
+        if (tsa_merge) {
+            if constexpr (sizeof(T) == 2) {
+                const bf16* Av[2] = {reinterpret_cast<const bf16*>(has_prev ? q0_t : q_in), e->prev_t.as<bf16>()};
+                bf16* Cv[2] = {reinterpret_cast<bf16*>(v_cur), reinterpret_cast<bf16*>(v_prev)};
+                e->launches++;
+                ProfScope ps(e, st, CAT_GEMM);
+                const int rc = fold_pos
+                    ? gemm_tc_tsa_inputs(Av, 1, w.tsa_v_wh.as<bf16>(), w.tsa_v_b.as<float>(), Cv, reinterpret_cast<const bf16*>(q_in),
+                                         nullptr, C, w.tsa_q_wh_fold.as<bf16>(), nullptr, w.tsa_q_const.as<float>(), (__half*)qproj,
+                                         Nq, nq_tsa, C, st)
+                    : gemm_tc_tsa_inputs(Av, has_prev ? 2 : 1, w.tsa_v_wh.as<bf16>(), w.tsa_v_b.as<float>(), Cv,
+                                         reinterpret_cast<const bf16*>(has_prev ? e->prev_t.as<T>() : q_in),
+                                         reinterpret_cast<const bf16*>(q_pos_in), C, w.tsa_q_wh.as<bf16>(), w.tsa_q_b.as<float>(),
+                                         nullptr, (__half*)qproj, Nq, nq_tsa, 2 * C, st);
+                if (rc) return 2;
+            }
+        } else {
         if (value_gemm(has_prev ? q0_t : q_in, v_cur)) return 2;
         if (has_prev) {
-            v_prev = e->tsa_value_prev.as<T>();
             if (value_gemm(e->prev_t.as<T>(), v_prev)) return 2;
         }
         if (fold_pos) {
@@ -361,6 +382,7 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
                                                    nullptr, (float*)qproj, Nq, nq_tsa, 2 * C, ACT_NONE, st);
             if (rc) return 2;
         }
+        }   // (tsa_merge)
         {
             ProfScope ps(e, st, CAT_TSA);
             if (tsa_hm) {

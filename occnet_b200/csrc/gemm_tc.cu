@@ -81,19 +81,41 @@ struct LnArgs {                                           // fused LayerNorm epi
     float* y_f32; bf16* y_bf16; bf16* y_pos_bf16;
 };
 
+// One GEMM problem of a launch.  A launch carries up to MAX_PROBS INDEPENDENT problems (e.g. TSA's value projection and
+// sampling-offset projection of the same query tensor): the CTAs [cta_begin, cta_begin + cta_count) work on problem p.  These
+// GEMMs have only ~2 tiles per CTA on 148 SMs, so their duration is start-up + a latency chain, not bandwidth: two problems on
+// 74 + 74 CTAs finish in about the time ONE took on 148.
 // w_resident: all nk weight k-blocks of this CTA's n-block stay in shared memory for the CTA's lifetime and the
 // ring only carries A tiles; otherwise each stage carries an A tile and a W k-block (v1 behaviour).
+constexpr int MAX_PROBS = 3;
+struct GemmProb {
+    CUtensorMap tmA, tmA2, tmW, tmC;
+    const float* bias; const float* residual; void* C;
+    long long ldc, nblk_stride;
+    int c_tma /* 0: none, 1: [M,N] row-major, 2: n-blocks as separate [M,BN] matrices,
+                 3: head-major value maps [n-block][column/32][M][32] (one 64-byte row per (head, token)) */;
+    int stg_bytes, M, N, BN, nk, nk1, act, w_resident, stages;
+    int out_half;                                             // 16-bit outputs as fp16 instead of bf16 (runtime, per problem)
+    int cta_begin, cta_count;
+};
+struct GemmProbs { GemmProb p[MAX_PROBS]; int n; };
+
 template <typename TC, bool LN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)          // 10 warps -> 3 on one SMSP -> <= 168 regs (16K per SMSP)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-               const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmC,
-               int c_tma /* 0: none, 1: [M,N] row-major, 2: n-blocks as separate [M,BN] matrices,
-                            3: head-major value maps [n-block][column/32][M][32] (one 64-byte row per (head, token)) */, int stg_bytes,
-               const float* __restrict__ bias,
-               const float* __restrict__ residual, TC* __restrict__ C, LnArgs ln, int M, int N, int BN, int nk,
-               int nk1, int act, int w_resident, int stages, long long ldc, long long nblk_stride,
-               long long* __restrict__ dbg)
+gemm_tc_kernel(const __grid_constant__ GemmProbs probs, LnArgs ln, long long* __restrict__ dbg)
 {
+    int pi = 0;
+    while (pi + 1 < probs.n && (int)blockIdx.x >= probs.p[pi + 1].cta_begin) ++pi;
+    const GemmProb& P = probs.p[pi];
+    const CUtensorMap& tmA = P.tmA; const CUtensorMap& tmA2 = P.tmA2; const CUtensorMap& tmW = P.tmW; const CUtensorMap& tmC = P.tmC;
+    const float* __restrict__ bias = P.bias;
+    const float* __restrict__ residual = P.residual;
+    TC* __restrict__ C = reinterpret_cast<TC*>(P.C);
+    const int c_tma = P.c_tma, stg_bytes = P.stg_bytes, M = P.M, N = P.N, BN = P.BN, nk = P.nk, nk1 = P.nk1, act = P.act;
+    const int w_resident = P.w_resident, stages = P.stages;
+    const long long ldc = P.ldc, nblk_stride = P.nblk_stride;
+    const bool out_half = std::is_same<TC, __half>::value || P.out_half != 0;
+    const int bid = (int)blockIdx.x - P.cta_begin, nctas = P.cta_count;
     // optional in-kernel timeline (globaltimer ns): 16 slots per CTA, written by the role that owns the event
     auto stamp = [&](int slot) {
         if (dbg) {
@@ -130,8 +152,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // rows are dealt out in 32-row blocks so that every CTA gets (almost) the same number of ROWS.  With whole
     // 128-row tiles, 313 tiles on 148 CTAs meant 3 tile-epilogues for some CTAs and 2 for the rest (70 % balance);
     // with row ranges the last tile of a CTA is partial and its (memory-bound) epilogue only touches the rows it owns.
-    const int n_blk = blockIdx.x % n_tiles;
-    const int grp = blockIdx.x / n_tiles, ngrp = gridDim.x / n_tiles;
+    const int n_blk = bid % n_tiles;
+    const int grp = bid / n_tiles, ngrp = nctas / n_tiles;
     const int nb32 = (M + 31) >> 5;
     const int row_begin = (int)(((long long)nb32 * grp) / ngrp) << 5;
     const int row_end = min(M, (int)(((long long)nb32 * (grp + 1)) / ngrp) << 5);
@@ -395,7 +417,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             float x0 = __uint_as_float(r[4 * j]) + b4.x, x1 = __uint_as_float(r[4 * j + 1]) + b4.y;
                             float x2 = __uint_as_float(r[4 * j + 2]) + b4.z, x3 = __uint_as_float(r[4 * j + 3]) + b4.w;
                             if (act == ACT_RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
-                            if constexpr (std::is_same<TC, __half>::value) {
+                            if (out_half) {
                                 const __half2 a = __floats2half2_rn(x0, x1), b = __floats2half2_rn(x2, x3);
                                 pk[2 * j] = *reinterpret_cast<const uint32_t*>(&a); pk[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&b);
                             } else {
@@ -454,7 +476,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const size_t o = (size_t)n_blk * nblk_stride + (size_t)grow * ldc + c0 + cpiece * 4;
                             if constexpr (sizeof(TC) == 4) {
                                 *reinterpret_cast<float4*>(reinterpret_cast<float*>(C) + o) = v;
-                            } else if constexpr (std::is_same<TC, __half>::value) {
+                            } else if (out_half) {
                                 const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
                                 *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(C) + o) =
                                     make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
@@ -585,10 +607,10 @@ int cached_map_out_heads(const void* base, uint64_t rows, uint64_t heads, uint64
     return 0;
 }
 
+// Fills one problem (tensor maps, plan, CTA share).  ctas = number of CTAs this problem may use (0: all SMs).
 template <typename TC, bool LN>
-int launch(const bf16* A, const bf16* A2, int K1, const bf16* W, const float* bias, const float* residual, TC* C,
-           LnArgs ln, int M, int N, int K, int act, cudaStream_t stream, bool blocked_out = false, int lda = 0, int lda2 = 0,
-           bool head_major = false)
+int build_prob(GemmProb& P, int& smem, const bf16* A, const bf16* A2, int K1, const bf16* W, const float* bias, const float* residual,
+               TC* C, int M, int N, int K, int act, bool blocked_out, int lda, int lda2, bool head_major, int ctas, int cta_begin)
 {
     if (A2 == nullptr) K1 = K;
     // 16-bit outputs without a residual leave through TMA stores of [32 rows x 32 columns] (OCC_GEMM_NO_TMA_STORE=1:
@@ -598,33 +620,48 @@ int launch(const bf16* A, const bf16* A2, int K1, const bf16* W, const float* bi
     const int stg_bytes = use_tma_store ? 2048 : 4096;
     const Plan p = make_plan(N, K, LN, stg_bytes);
     OCC_CHECK(p.BN > 0 && p.stages >= 2 && K % 64 == 0 && K1 % 64 == 0 && M > 0, "gemm_tc: unsupported shape");
-    CUtensorMap tmA, tmA2, tmW;
-    if (cached_map_2d(A, (uint64_t)K1, (uint64_t)M, BLOCK_K, BLOCK_M, &tmA, (uint64_t)lda)) return 1;
-    if (A2) { if (cached_map_2d(A2, (uint64_t)(K - K1), (uint64_t)M, BLOCK_K, BLOCK_M, &tmA2, (uint64_t)lda2)) return 1; }
-    else tmA2 = tmA;
-    if (cached_map_2d(W, (uint64_t)K, (uint64_t)N, BLOCK_K, (uint32_t)p.BN, &tmW)) return 1;
-    CUtensorMap tmC = tmW;
-    int c_tma = 0;
+    if (cached_map_2d(A, (uint64_t)K1, (uint64_t)M, BLOCK_K, BLOCK_M, &P.tmA, (uint64_t)lda)) return 1;
+    if (A2) { if (cached_map_2d(A2, (uint64_t)(K - K1), (uint64_t)M, BLOCK_K, BLOCK_M, &P.tmA2, (uint64_t)lda2)) return 1; }
+    else P.tmA2 = P.tmA;
+    if (cached_map_2d(W, (uint64_t)K, (uint64_t)N, BLOCK_K, (uint32_t)p.BN, &P.tmW)) return 1;
+    P.tmC = P.tmW;
+    P.c_tma = 0;
     if (use_tma_store) {
         const uint32_t box_cols = 32u;
         if (head_major) {
-            if (cached_map_out_heads(C, (uint64_t)M, (uint64_t)(p.BN / 32), (uint64_t)(N / p.BN), &tmC)) return 1;
-            c_tma = 3;
+            if (cached_map_out_heads(C, (uint64_t)M, (uint64_t)(p.BN / 32), (uint64_t)(N / p.BN), &P.tmC)) return 1;
+            P.c_tma = 3;
         } else if (blocked_out) {
-            if (cached_map_out(C, (uint64_t)p.BN, (uint64_t)M, (uint64_t)(N / p.BN), box_cols, &tmC)) return 1;
-            c_tma = 2;
+            if (cached_map_out(C, (uint64_t)p.BN, (uint64_t)M, (uint64_t)(N / p.BN), box_cols, &P.tmC)) return 1;
+            P.c_tma = 2;
         } else {
-            if (cached_map_out(C, (uint64_t)N, (uint64_t)M, 1, box_cols, &tmC)) return 1;
-            c_tma = 1;
+            if (cached_map_out(C, (uint64_t)N, (uint64_t)M, 1, box_cols, &P.tmC)) return 1;
+            P.c_tma = 1;
         }
     }
-    const int num_sms = sm_count_current_device();
+    if (ctas <= 0) ctas = sm_count_current_device();
+    const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = N / p.BN;
+    int per_n = ctas / n_tiles;
+    if (per_n > m_tiles) per_n = m_tiles;                        // (row ranges are dealt in 32-row blocks: >= 1 per CTA)
+    OCC_CHECK(per_n >= 1, "gemm_tc: fewer CTAs than n-blocks");
+    P.bias = bias; P.residual = residual; P.C = C;
+    P.ldc = blocked_out ? (long long)p.BN : (long long)N;
+    P.nblk_stride = blocked_out ? (long long)M * p.BN : (long long)p.BN;
+    P.stg_bytes = stg_bytes; P.M = M; P.N = N; P.BN = p.BN; P.nk = K / BLOCK_K; P.nk1 = K1 / BLOCK_K; P.act = act;
+    P.w_resident = p.resident; P.stages = p.stages;
+    P.out_half = std::is_same<TC, __half>::value ? 1 : 0;
+    P.cta_begin = cta_begin; P.cta_count = per_n * n_tiles;
+    smem = p.smem;
+    return 0;
+}
+
+template <typename TC, bool LN>
+int launch_probs(const GemmProbs& probs, int smem, LnArgs ln, cudaStream_t stream)
+{
     // per-device attribute (cheap): a process-wide `static bool` would leave a second device without the opt-in
     OCC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<TC, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = N / p.BN;
-    int per_n = num_sms / n_tiles;
-    if (per_n > m_tiles) per_n = m_tiles;                        // (row ranges are dealt in 32-row blocks: >= 1 per CTA)
-    const int grid = per_n * n_tiles;
+    const GemmProb& last = probs.p[probs.n - 1];
+    const int grid = last.cta_begin + last.cta_count;
     long long* dbg = nullptr;
     static const bool want_dbg = getenv("OCC_GEMM_TIMELINE") != nullptr;
     if (want_dbg) {
@@ -633,16 +670,12 @@ int launch(const bf16* A, const bf16* A2, int K1, const bf16* W, const float* bi
     }
     {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = p.smem; cfg.stream = stream;
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        const int nk = K / BLOCK_K, nk1 = K1 / BLOCK_K, res = p.resident, stg = p.stages;
-        const long long ldc = blocked_out ? (long long)p.BN : (long long)N;
-        const long long nbs = blocked_out ? (long long)M * p.BN : (long long)p.BN;
-        OCC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<TC, LN>, tmA, tmA2, tmW, tmC, c_tma, stg_bytes, bias, residual, C, ln, M, N, p.BN, nk, nk1,
-                                    act, res, stg, ldc, nbs, dbg));
+        OCC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<TC, LN>, probs, ln, dbg));
     }
     OCC_CUDA(cudaGetLastError());
     if (want_dbg) {                                               // development aid: per-CTA timeline in ns
@@ -652,8 +685,10 @@ int launch(const bf16* A, const bf16* A2, int K1, const bf16* W, const float* bi
         cudaFree(dbg);
         long long t0 = h[0];
         for (int b = 0; b < grid; ++b) if (h[(size_t)b * 16] && h[(size_t)b * 16] < t0) t0 = h[(size_t)b * 16];
-        fprintf(stderr, "[gemm timeline] M=%d N=%d K=%d BN=%d resident=%d stages=%d grid=%d LN=%d\n", M, N, K, p.BN,
-                p.resident, p.stages, grid, (int)LN);
+        for (int q = 0; q < probs.n; ++q)
+            fprintf(stderr, "[gemm timeline] problem %d: M=%d N=%d K=%d BN=%d resident=%d stages=%d ctas=%d LN=%d\n", q, probs.p[q].M,
+                    probs.p[q].N, probs.p[q].nk * BLOCK_K, probs.p[q].BN, probs.p[q].w_resident, probs.p[q].stages,
+                    probs.p[q].cta_count, (int)LN);
         const int show[] = {0, 1, grid / 2, grid - 1};
         for (int b : show) {
             fprintf(stderr, "  cta %3d:", b);
@@ -662,6 +697,19 @@ int launch(const bf16* A, const bf16* A2, int K1, const bf16* W, const float* bi
         }
     }
     return 0;
+}
+
+template <typename TC, bool LN>
+int launch(const bf16* A, const bf16* A2, int K1, const bf16* W, const float* bias, const float* residual, TC* C,
+           LnArgs ln, int M, int N, int K, int act, cudaStream_t stream, bool blocked_out = false, int lda = 0, int lda2 = 0,
+           bool head_major = false)
+{
+    GemmProbs probs;
+    probs.n = 1;
+    int smem = 0;
+    if (build_prob<TC, LN>(probs.p[0], smem, A, A2, K1, W, bias, residual, C, M, N, K, act, blocked_out, lda, lda2, head_major, 0, 0))
+        return 1;
+    return launch_probs<TC, LN>(probs, smem, ln, stream);
 }
 
 }  // namespace
@@ -713,6 +761,38 @@ int gemm_tc_ln(const bf16* A, const bf16* W, const float* bias, const float* res
     OCC_CHECK(y_pos_bf16 == nullptr || pos != nullptr, "gemm_tc_ln: pos required for y_pos");
     return launch<float, true>(A, nullptr, 0, W, bias, residual, (float*)nullptr, LnArgs{gamma, beta, pos, y_f32, y_bf16, y_pos_bf16},
                                M, 256, K, ACT_NONE, stream);
+}
+
+// Two (or three) independent 16-bit-output GEMMs in ONE launch: the CTAs are shared out in proportion to N.K.
+//   value problems: Cv[i] = Av[i].Wv^T + bv (bf16, [M,256], TMA-store epilogue), i < nv <= 2  (TSA value_proj of each queue entry)
+//   projection    : Cq = [Aq | Aq2].Wq^T + bq (+ rq, fp32 [M,Nq]) as fp16                  (sampling offsets + attention logits)
+int gemm_tc_tsa_inputs(const bf16* const* Av, int nv, const bf16* Wv, const float* bv, bf16* const* Cv, const bf16* Aq,
+                       const bf16* Aq2, int K1q, const bf16* Wq, const float* bq, const float* rq, __half* Cq, int M, int Nq,
+                       int Kq, cudaStream_t stream)
+{
+    OCC_CHECK(nv >= 1 && nv <= 2, "gemm_tc_tsa_inputs: 1 or 2 value problems");
+    const int num_sms = sm_count_current_device();
+    const double wv = 256.0 * 256.0, wq = (double)Nq * Kq, tot = nv * wv + wq;
+    int cq = (int)(num_sms * wq / tot + 0.5);
+    const int nq_tiles = Nq / make_plan(Nq, Kq, false, rq ? 4096 : 2048).BN;
+    if (cq < nq_tiles) cq = nq_tiles;
+    const int cv = (num_sms - cq) / nv;
+    OCC_CHECK(cv >= 1, "gemm_tc_tsa_inputs: not enough SMs");
+    GemmProbs probs;
+    probs.n = nv + 1;
+    int smem = 0, sm = 0, begin = 0;
+    for (int i = 0; i < nv; ++i) {
+        if (build_prob<bf16, false>(probs.p[i], sm, Av[i], nullptr, 0, Wv, bv, nullptr, Cv[i], M, 256, 256, ACT_NONE, false, 0, 0,
+                                    false, cv, begin)) return 1;
+        begin += probs.p[i].cta_count;
+        smem = sm > smem ? sm : smem;
+    }
+    // (built through the bf16 instantiation: out_half selects the fp16 packing at run time)
+    if (build_prob<bf16, false>(probs.p[nv], sm, Aq, Aq2, K1q, Wq, bq, rq, reinterpret_cast<bf16*>(Cq), M, Nq, Kq, ACT_NONE, false,
+                                0, 0, false, cq, begin)) return 1;
+    probs.p[nv].out_half = 1;
+    smem = sm > smem ? sm : smem;
+    return launch_probs<bf16, false>(probs, smem, LnArgs{}, stream);
 }
 
 template int gemm_tc<float>(const bf16*, const bf16*, int, const bf16*, const float*, const float*, float*, int, int,

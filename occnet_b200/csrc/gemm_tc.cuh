@@ -24,6 +24,13 @@ int gemm_tc_ln(const bf16* A, const bf16* W, const float* bias, const float* res
 int gemm_tc_blocked256(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, int N, int K, cudaStream_t stream,
                        bool head_major = false);
 
+// TemporalSelfAttention's input projections in ONE launch (independent problems on disjoint CTAs): value_proj of 1-2 queue
+// entries (bf16 [M,256]) + the concatenated sampling_offsets / attention_weights projection (fp16 [M,Nq], optional fp32
+// epilogue constant rq [M,Nq], optional second K operand Aq2)
+int gemm_tc_tsa_inputs(const bf16* const* Av, int nv, const bf16* Wv, const float* bv, bf16* const* Cv, const bf16* Aq,
+                       const bf16* Aq2, int K1q, const bf16* Wq, const float* bq, const float* rq, __half* Cq, int M, int Nq,
+                       int Kq, cudaStream_t stream);
+
 int gemm_tc_heads256(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, int K, cudaStream_t stream);
 
 // fp32-grade product of an fp32 operand (given as its bf16 split S = [hi | lo], [M, 2*Ks]) with fp32 weights (given as

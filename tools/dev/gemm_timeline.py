@@ -1,13 +1,25 @@
-import torch, os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-from occnet_b200 import _lib
-lib = _lib.load()
-torch.manual_seed(0)
-for (M, N, K) in [(40000, 256, 256), (184950, 256, 256), (40000, 768, 256)]:
-    A = (torch.randn(M, K, device='cuda') * 0.5).bfloat16()
-    W = (torch.randn(N, K, device='cuda') * 0.1).bfloat16()
-    b = torch.randn(N, device='cuda')
-    C = torch.empty((M, N), device='cuda')
-    for _ in range(2):
-        _lib.check(lib.occb200_gemm_bf16_tc(_lib.ptr(A), _lib.ptr(W), _lib.ptr(b), _lib.ptr(C), M, N, K, _lib.stream_ptr()))
-        torch.cuda.synchronize()
+"""In-kernel globaltimer timeline of every tcgen05 GEMM launch of ONE frame (OCC_GEMM_TIMELINE=1 makes every launch synchronous and
+prints per-CTA stamps: 0 start, 1 setup done, 2 MMA warp ready, 3/6/9 first A block of tile 0/1/2 landed, 4/7/10 accumulator ready,
+5/8/11 epilogue done, 15 end; ns relative to the earliest CTA start).  Usage: python tools/dev/gemm_timeline.py 2> timeline.log"""
+import os
+import sys
+
+os.environ['OCC_GEMM_TIMELINE'] = '1'
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from occnet_b200 import fixtures                    # noqa: E402
+from occnet_b200.engine import OccEngine            # noqa: E402
+
+cfg = fixtures.make_cfg('full', num_layers=2)
+params = fixtures.init_params(cfg, seed=2, free_bias=fixtures.FREE_BIAS)
+metas = fixtures.make_img_metas(cfg)
+frames = [f[0].bfloat16().to('cuda:0').contiguous() for f in fixtures.make_feats(cfg, bs=1, seed=100)]
+eng = OccEngine(cfg, params, precision='bf16', use_tensor_cores=True, device='cuda:0')
+eng.set_cameras(metas)
+eng.set_input_dtype(torch.bfloat16)
+for i in range(3):
+    sys.stderr.write(f'==== frame {i}\n')
+    eng.forward(frames, want=('flow', 'occ_cls'))
+torch.cuda.synchronize()
