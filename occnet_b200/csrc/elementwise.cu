@@ -163,13 +163,15 @@ __global__ void bev_pos_kernel(const float* __restrict__ row_embed, const float*
     pos[i] = (c < half) ? col_embed[x * half + c] : row_embed[y * half + (c - half)];
 }
 
-// row-major [rows,256] <-> T32 (dir 0: tile, 1: untile); one thread per 4 floats
-__global__ void t32_convert_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t rows, int dir)
+// row-major [rows,ncols] <-> T32 (dir 0: tile, 1: untile); one thread per 4 floats; ncols a multiple of 32 (256: the residual stream)
+__global__ void t32_convert_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t rows, int dir, int ncols)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows * 64) return;
-    const int64_t row = i >> 6; const int col = (int)(i & 63) * 4;
-    const int64_t a = row * 256 + col, b = t32_index(row, col);
+    const int q4 = ncols >> 2;
+    if (i >= rows * q4) return;
+    const int64_t row = i / q4; const int col = (int)(i % q4) * 4;
+    const int64_t a = row * ncols + col;
+    const int64_t b = ((((row >> 5) * (ncols >> 5) + (col >> 5)) * 8 + ((col & 31) >> 2)) * 32 + (row & 31)) * 4 + (col & 3);
     if (dir == 0) *reinterpret_cast<float4*>(dst + b) = __ldg(reinterpret_cast<const float4*>(src + a));
     else          *reinterpret_cast<float4*>(dst + a) = __ldg(reinterpret_cast<const float4*>(src + b));
 }
@@ -242,9 +244,10 @@ int launch_bev_pos(const float* row_embed, const float* col_embed, int bev_h, in
     return 0;
 }
 
-int launch_t32_convert(const float* src, float* dst, int64_t rows, int untile, cudaStream_t stream)
+int launch_t32_convert(const float* src, float* dst, int64_t rows, int untile, cudaStream_t stream, int ncols)
 {
-    t32_convert_kernel<<<ceil_div(rows * 64, 256), 256, 0, stream>>>(src, dst, rows, untile);
+    OCC_CHECK(ncols > 0 && ncols % 32 == 0, "t32_convert: ncols must be a multiple of 32");
+    t32_convert_kernel<<<ceil_div(rows * (ncols / 4), 256), 256, 0, stream>>>(src, dst, rows, untile, ncols);
     OCC_CUDA(cudaGetLastError());
     return 0;
 }

@@ -51,7 +51,7 @@ struct LayerW {
     DevBuf tsa_v_wh, tsa_q_wh, tsa_o_wh, sca_q_wh, sca_v_wh, sca_o_wh, ffn1_wh, ffn2_wh;
     // self mode (prev_bev = None): W1 q + W2 (q + pos) + b == (W1 + W2) q + [W2 pos + b]; the bracket depends on parameters
     // only -> an fp32 [Nq,192] constant per layer, added by the GEMM epilogue (K = 256, weight block resident, A read once)
-    DevBuf tsa_q_wh_fold, tsa_q_const;
+    DevBuf tsa_q_wh_fold, tsa_q_const, tsa_q_const_t32;   // (_t32: the constant in the T32 block layout, TMA-store epilogue)
 };
 
 }  // namespace
@@ -317,11 +317,20 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
         if (gemm_tc_blocked256((const bf16*)tokens, e->sca_v_all_wh.as<bf16>(), e->sca_v_all_b.as<float>(),
                                e->sca_value_all.as<bf16>(), ncam * Nv, c.num_layers * C, C, st, e->value_head_major)) return 2;
     }
+    // Chained dense layers (gemm_chain.cu): [TSA output_proj+LN -> SCA sampling projection] and [SCA output_proj+LN -> FFN1 ->
+    // FFN2+LN -> next layer's TSA value / sampling projections] are ONE persistent launch each (OCC_GEMM_CHAIN=0: one launch
+    // per layer, gemm_tc.cu)
+    static const bool chain_env = getenv("OCC_GEMM_CHAIN") == nullptr || atoi(getenv("OCC_GEMM_CHAIN")) != 0;
+    const bool use_chain = sizeof(T) == 2 && fuse_ln && q_half && chain_env && mode == MODE_FRAME && !e->value_head_major;
+    static const bool tsa_merge_env0 = getenv("OCC_TSA_MERGE") == nullptr || atoi(getenv("OCC_TSA_MERGE")) != 0;
+    const bool tsa_merge_ok = tsa_merge_env0;
+    bool tsa_inputs_done = false;           // this layer's TSA value / sampling projections were written by the previous chain
     for (int l = 0; l < c.num_layers; ++l) {
         LayerW& w = e->layers[l];
         // self mode (prev_bev = None): W1 q + W2 (q + pos) = (W1 + W2) q + W2 pos -- the second operand is the CONSTANT
         // bf16 pos, so no layer has to write (and the FFN LayerNorm epilogue has to read pos for) a bf16 copy of q + pos
         const bool fold_pos = fuse_ln && !has_prev && w.tsa_q_wh_fold.p != nullptr && w.tsa_q_const.p != nullptr && q_half;
+        bool sca_q_done = false;                                // the SCA sampling projection was the tail of the TSA chain
         // ---- temporal self-attention (temporal_self_attention.py:177-272)
         if (l == 0 && l0_fold) {
             // precomputed at finalize: residual stream := constant T32 buffer, SCA projection operand := constant bf16 copy
@@ -350,7 +359,9 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
         static const bool tsa_merge_env = getenv("OCC_TSA_MERGE") == nullptr || atoi(getenv("OCC_TSA_MERGE")) != 0;
         const bool tsa_merge = sizeof(T) == 2 && fuse_ln && q_half && !tsa_hm && tsa_merge_env && w.tsa_v_wh.p != nullptr;
         if (has_prev) v_prev = e->tsa_value_prev.as<T>();
-        if (tsa_merge) {
+        if (tsa_inputs_done) {
+            tsa_inputs_done = false;                             // (written by the tail of the previous layer's chain)
+        } else if (tsa_merge) {
             if constexpr (sizeof(T) == 2) {
                 const bf16* Av[2] = {reinterpret_cast<const bf16*>(has_prev ? q0_t : q_in), e->prev_t.as<bf16>()};
                 bf16* Cv[2] = {reinterpret_cast<bf16*>(v_cur), reinterpret_cast<bf16*>(v_prev)};
@@ -358,12 +369,12 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
                 ProfScope ps(e, st, CAT_GEMM);
                 const int rc = fold_pos
                     ? gemm_tc_tsa_inputs(Av, 1, w.tsa_v_wh.as<bf16>(), w.tsa_v_b.as<float>(), Cv, reinterpret_cast<const bf16*>(q_in),
-                                         nullptr, C, w.tsa_q_wh_fold.as<bf16>(), nullptr, w.tsa_q_const.as<float>(), (__half*)qproj,
-                                         Nq, nq_tsa, C, st)
+                                         nullptr, C, w.tsa_q_wh_fold.as<bf16>(), nullptr, w.tsa_q_const.as<float>(),
+                                         w.tsa_q_const_t32.as<float>(), (__half*)qproj, Nq, nq_tsa, C, st)
                     : gemm_tc_tsa_inputs(Av, has_prev ? 2 : 1, w.tsa_v_wh.as<bf16>(), w.tsa_v_b.as<float>(), Cv,
                                          reinterpret_cast<const bf16*>(has_prev ? e->prev_t.as<T>() : q_in),
                                          reinterpret_cast<const bf16*>(q_pos_in), C, w.tsa_q_wh.as<bf16>(), w.tsa_q_b.as<float>(),
-                                         nullptr, (__half*)qproj, Nq, nq_tsa, 2 * C, st);
+                                         nullptr, nullptr, (__half*)qproj, Nq, nq_tsa, 2 * C, st);
                 if (rc) return 2;
             }
         } else {
@@ -391,6 +402,23 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
             } else if (launch_tsa_fused<T>(v_prev, v_cur, qproj, q_half, c.bev_h, c.bev_w, attn_out, st)) return 2;
         }
         e->launches++;
+        if (use_chain) {
+            if constexpr (sizeof(T) == 2) {
+                GemmChainOp ops[2];
+                memset(ops, 0, sizeof(ops));
+                ops[0].A = reinterpret_cast<const bf16*>(attn_out); ops[0].K1 = C; ops[0].W = w.tsa_o_wh.as<bf16>(); ops[0].N = C; ops[0].K = C;
+                ops[0].bias = w.tsa_o_b.as<float>(); ops[0].ln = 1; ops[0].residual = q_f32; ops[0].gamma = w.ln_g[0].as<float>();
+                ops[0].beta = w.ln_b[0].as<float>(); ops[0].y_f32 = x_f32; ops[0].y_bf16 = reinterpret_cast<bf16*>(q_t);
+                ops[1].A = reinterpret_cast<const bf16*>(q_t); ops[1].K1 = C; ops[1].W = w.sca_q_wh.as<bf16>(); ops[1].N = nq_sca; ops[1].K = C;
+                ops[1].bias = w.sca_q_b.as<float>(); ops[1].dep = 1; ops[1].C = qproj; ops[1].out_half = 1; ops[1].act = ACT_NONE;
+                e->launches++;
+                ProfScope ps(e, st, CAT_GEMM);
+                if (gemm_chain_launch(ops, 2, Nq, st)) return 2;
+            }
+            advance();
+            q_in = q_t; q_pos_in = q_pos_t;
+            sca_q_done = true;
+        } else
         if (fuse_ln) {
             float* y32 = mode == MODE_L0_TSA_ONLY ? e->l0_x_f32.as<float>() : x_f32;
             bf16* y16 = mode == MODE_L0_TSA_ONLY ? e->l0_q_t.as<bf16>() : (bf16*)q_t;
@@ -414,7 +442,9 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
         }
         }   // (layer-0 TSA fold)
         // ---- spatial cross-attention (spatial_cross_attention.py:128-175, :334-393)
-        {
+        if (sca_q_done) {
+            q_t_in = q_t;
+        } else {
             const int rc = q_half ? gemm<T, __half>(e, q_t_in, nullptr, 0, w.sca_q_w.as<float>(), w.sca_q_wh.p, w.sca_q_b.as<float>(),
                                                     nullptr, (__half*)qproj, Nq, nq_sca, C, ACT_NONE, st)
                                   : gemm<T, float>(e, q_t_in, nullptr, 0, w.sca_q_w.as<float>(), w.sca_q_wh.p, w.sca_q_b.as<float>(),
@@ -437,6 +467,42 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
                                            e->sca_sched.as<unsigned>())) return 2;
         }
         e->launches++;
+        if (use_chain) {
+            if constexpr (sizeof(T) == 2) {
+                GemmChainOp ops[5];
+                memset(ops, 0, sizeof(ops));
+                int n = 0;
+                const bool need_qpos = !fold_pos;
+                ops[n].A = reinterpret_cast<const bf16*>(attn_out); ops[n].K1 = C; ops[n].W = w.sca_o_wh.as<bf16>(); ops[n].N = C; ops[n].K = C;
+                ops[n].bias = w.sca_o_b.as<float>(); ops[n].ln = 1; ops[n].residual = q_f32; ops[n].gamma = w.ln_g[1].as<float>();
+                ops[n].beta = w.ln_b[1].as<float>(); ops[n].y_f32 = x_f32; ops[n].y_bf16 = reinterpret_cast<bf16*>(q_t);
+                ++n; advance();
+                ops[n].A = reinterpret_cast<const bf16*>(q_t); ops[n].K1 = C; ops[n].W = w.ffn1_wh.as<bf16>(); ops[n].N = c.ffn_dim; ops[n].K = C;
+                ops[n].bias = w.ffn1_b.as<float>(); ops[n].dep = 1; ops[n].C = e->ffn_h.p; ops[n].act = ACT_RELU;
+                ++n;
+                ops[n].A = e->ffn_h.as<bf16>(); ops[n].K1 = c.ffn_dim; ops[n].W = w.ffn2_wh.as<bf16>(); ops[n].N = C; ops[n].K = c.ffn_dim;
+                ops[n].bias = w.ffn2_b.as<float>(); ops[n].dep = 1; ops[n].ln = 1; ops[n].residual = q_f32; ops[n].gamma = w.ln_g[2].as<float>();
+                ops[n].beta = w.ln_b[2].as<float>(); ops[n].y_f32 = x_f32; ops[n].y_bf16 = reinterpret_cast<bf16*>(q_t);
+                if (need_qpos) { ops[n].pos = e->pos_t32.as<float>(); ops[n].y_pos_bf16 = reinterpret_cast<bf16*>(q_pos_t); }
+                ++n; advance();
+                // next layer's TSA inputs (self mode): value_proj and the folded sampling projection read the LayerNorm output
+                if (l + 1 < c.num_layers && !has_prev && tsa_merge_ok) {
+                    LayerW& wn = e->layers[l + 1];
+                    if (wn.tsa_q_wh_fold.p && wn.tsa_q_const_t32.p && wn.tsa_v_wh.p) {
+                        ops[n].A = reinterpret_cast<const bf16*>(q_t); ops[n].K1 = C; ops[n].W = wn.tsa_v_wh.as<bf16>(); ops[n].N = C; ops[n].K = C;
+                        ops[n].bias = wn.tsa_v_b.as<float>(); ops[n].dep = 1; ops[n].C = e->tsa_value.p;
+                        ++n;
+                        ops[n].A = reinterpret_cast<const bf16*>(q_t); ops[n].K1 = C; ops[n].W = wn.tsa_q_wh_fold.as<bf16>(); ops[n].N = nq_tsa; ops[n].K = C;
+                        ops[n].dep = 1; ops[n].C = qproj; ops[n].out_half = 1; ops[n].res_t32 = wn.tsa_q_const_t32.as<float>();
+                        ++n;
+                        tsa_inputs_done = true;
+                    }
+                }
+                e->launches++;
+                ProfScope ps(e, st, CAT_GEMM);
+                if (gemm_chain_launch(ops, n, Nq, st)) return 2;
+            }
+        } else
         if (fuse_ln) {
             if (gemm_ln_fused(e, (const bf16*)attn_out, w.sca_o_wh.p, w.sca_o_b.as<float>(), q_f32, w.ln_g[1].as<float>(),
                               w.ln_b[1].as<float>(), nullptr, x_f32, (bf16*)q_t, nullptr, Nq, C, st)) return 2;
@@ -455,6 +521,9 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
             e->launches++;
         }
         // ---- FFN (mmcv FFN: x + W2 relu(W1 x))
+        if (use_chain) {
+            // (FFN1, FFN2 + LayerNorm were ops 1-2 of the chain above)
+        } else {
         if (gemm<T, T>(e, q_t, nullptr, 0, w.ffn1_w.as<float>(), w.ffn1_wh.p, w.ffn1_b.as<float>(), nullptr,
                        e->ffn_h.as<T>(), Nq, c.ffn_dim, C, ACT_RELU, st)) return 2;
         if (fuse_ln) {
@@ -474,6 +543,7 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
             }
             e->launches++;
         }
+        }   // (!use_chain)
         if (e->taps)
             OCC_CUDA(cudaMemcpyAsync(e->tap_layer.as<float>() + (size_t)l * Nq * C, q_f32, (size_t)Nq * C * 4,
                                      cudaMemcpyDeviceToDevice, st));
@@ -603,7 +673,7 @@ void occb200_engine_destroy(occb200_engine* e)
                          &w.sca_v_w, &w.sca_v_b, &w.sca_o_w, &w.sca_o_b, &w.ffn1_w, &w.ffn1_b, &w.ffn2_w, &w.ffn2_b,
                          &w.ln_g[0], &w.ln_g[1], &w.ln_g[2], &w.ln_b[0], &w.ln_b[1], &w.ln_b[2], &w.tsa_v_wh,
                          &w.tsa_q_wh, &w.tsa_o_wh, &w.sca_q_wh, &w.sca_v_wh, &w.sca_o_wh, &w.ffn1_wh, &w.ffn2_wh,
-                         &w.tsa_q_wh_fold, &w.tsa_q_const};
+                         &w.tsa_q_wh_fold, &w.tsa_q_const, &w.tsa_q_const_t32};
         for (DevBuf* b : all) b->release();
     }
     DevBuf* all[] = {&e->sca_sched, &e->rot_map, &e->split_ws, &e->tokens_split, &e->l0_x_f32, &e->l0_q_t, &e->pos_bf, &e->qc_f32, &e->qc_t, &e->qc_pos_t, &e->bev_queries, &e->pos, &e->pos_t32, &e->cams_embeds, &e->level_embeds, &e->conv_w[0], &e->conv_w[1],
@@ -725,6 +795,13 @@ int occb200_engine_finalize(occb200_engine* e)
                 if (gemm_simt<float, float>(e->pos.as<float>(), (int)half, nullptr, 0, (int)half, w2.as<float>(), bbuf.as<float>(),
                                             nullptr, (int)rows, fold_const->as<float>(), (int)rows, Nq, (int)rows, (int)half,
                                             ACT_NONE, 0)) return 2;
+                // the same constant in the T32 block layout (rows padded to 32) for the TMA-store epilogue of the merged launch
+                if (rows % 32 == 0) {
+                    const size_t rows_pad = ((size_t)Nq + 31) / 32 * 32;
+                    if (w.tsa_q_const_t32.alloc(rows_pad * rows * 4)) return 2;
+                    OCC_CUDA(cudaMemset(w.tsa_q_const_t32.p, 0, rows_pad * rows * 4));
+                    if (launch_t32_convert(fold_const->as<float>(), w.tsa_q_const_t32.as<float>(), Nq, 0, 0, (int)rows)) return 2;
+                }
                 OCC_CUDA(cudaDeviceSynchronize());
                 w2.release();
             }

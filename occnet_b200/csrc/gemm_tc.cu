@@ -65,6 +65,10 @@ int make_tensor_map_bf16(CUtensorMap* map, const void* base, int rank, const uin
     return 0;
 }
 
+int cached_map_2d(const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows, CUtensorMap* out,
+                  uint64_t ld = 0);
+int cached_map_out(const void* base, uint64_t cols, uint64_t rows, uint64_t blocks, uint32_t box_cols, CUtensorMap* out);
+
 namespace {
 
 constexpr int BLOCK_M = 128, BLOCK_K = 64, A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
@@ -91,6 +95,8 @@ constexpr int MAX_PROBS = 3;
 struct GemmProb {
     CUtensorMap tmA, tmA2, tmW, tmC;
     const float* bias; const float* residual; void* C;
+    const float* res_t32;                                     // optional fp32 epilogue constant [M,N] in the T32 block layout
+                                                              // (TMA-store path: the row-per-thread read is then coalesced)
     long long ldc, nblk_stride;
     int c_tma /* 0: none, 1: [M,N] row-major, 2: n-blocks as separate [M,BN] matrices,
                  3: head-major value maps [n-block][column/32][M][32] (one 64-byte row per (head, token)) */;
@@ -110,6 +116,7 @@ gemm_tc_kernel(const __grid_constant__ GemmProbs probs, LnArgs ln, long long* __
     const CUtensorMap& tmA = P.tmA; const CUtensorMap& tmA2 = P.tmA2; const CUtensorMap& tmW = P.tmW; const CUtensorMap& tmC = P.tmC;
     const float* __restrict__ bias = P.bias;
     const float* __restrict__ residual = P.residual;
+    const float* __restrict__ res_t32 = P.res_t32;
     TC* __restrict__ C = reinterpret_cast<TC*>(P.C);
     const int c_tma = P.c_tma, stg_bytes = P.stg_bytes, M = P.M, N = P.N, BN = P.BN, nk = P.nk, nk1 = P.nk1, act = P.act;
     const int w_resident = P.w_resident, stages = P.stages;
@@ -398,46 +405,41 @@ gemm_tc_kernel(const __grid_constant__ GemmProbs probs, LnArgs ln, long long* __
                 // 16-bit outputs: accumulator row -> bias/act -> packed 16-bit -> swizzled staging rows -> ONE TMA store
                 // per [32 rows x box] block.  No shared-memory read-back, no per-lane global stores: the LSU only sees
                 // the 16-byte STS of each thread's own row (conflict-free under the TMA swizzle).
-                const int box = stg_bytes >= 4096 && (ncol & 63) == 0 ? 64 : 32;   // columns per store (= tensor map box)
+                constexpr int box = 32;                          // columns per store (= tensor map box; 2 KB staging block per warp)
                 for (int c0 = cbeg; c0 < cbeg + ncol; c0 += box) {
                     const int col = n_blk * BN + c0;
-                    uint32_t r[64];
-                    {
-                        uint32_t (&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
-                        uint32_t (&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
-                        tc::tmem_ld32(taddr + c0, lo);
-                        if (box == 64) tc::tmem_ld32(taddr + c0 + 32, hi);
-                        tc::tmem_ld_wait();
-                    }
-                    uint32_t pk[32];
+                    float4 kq[8];                                // epilogue constant of this thread's row, 32 columns
+                    if (res_t32) {
+                        const float4* p4 = reinterpret_cast<const float4*>(res_t32) +
+                                           ((size_t)(row0 >> 5) * (N >> 5) + (size_t)(col >> 5)) * 256 + lane;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {               // 4 columns per step (bias is warp-uniform: broadcast loads)
-                        if (4 * j < box) {
-                            const float4 b4 = reinterpret_cast<const float4*>(cvec + c0)[j];
-                            float x0 = __uint_as_float(r[4 * j]) + b4.x, x1 = __uint_as_float(r[4 * j + 1]) + b4.y;
-                            float x2 = __uint_as_float(r[4 * j + 2]) + b4.z, x3 = __uint_as_float(r[4 * j + 3]) + b4.w;
-                            if (act == ACT_RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
-                            if (out_half) {
-                                const __half2 a = __floats2half2_rn(x0, x1), b = __floats2half2_rn(x2, x3);
-                                pk[2 * j] = *reinterpret_cast<const uint32_t*>(&a); pk[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&b);
-                            } else {
-                                pk[2 * j] = pack_bf16x2(x0, x1); pk[2 * j + 1] = pack_bf16x2(x2, x3);
-                            }
+                        for (int j = 0; j < 8; ++j) kq[j] = __ldg(p4 + j * 32);
+                    }
+                    uint32_t r[32];
+                    tc::tmem_ld32(taddr + c0, r);
+                    tc::tmem_ld_wait();
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {                // 4 columns per step (bias is warp-uniform: broadcast loads)
+                        const float4 b4 = reinterpret_cast<const float4*>(cvec + c0)[j];
+                        float x0 = __uint_as_float(r[4 * j]) + b4.x, x1 = __uint_as_float(r[4 * j + 1]) + b4.y;
+                        float x2 = __uint_as_float(r[4 * j + 2]) + b4.z, x3 = __uint_as_float(r[4 * j + 3]) + b4.w;
+                        if (res_t32) { x0 += kq[j].x; x1 += kq[j].y; x2 += kq[j].z; x3 += kq[j].w; }
+                        if (act == ACT_RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+                        if (out_half) {
+                            const __half2 a = __floats2half2_rn(x0, x1), b = __floats2half2_rn(x2, x3);
+                            pk[2 * j] = *reinterpret_cast<const uint32_t*>(&a); pk[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&b);
+                        } else {
+                            pk[2 * j] = pack_bf16x2(x0, x1); pk[2 * j + 1] = pack_bf16x2(x2, x3);
                         }
                     }
                     if (lane == 0) tc::tma_store_wait_read();    // the previous store has drained the staging block
                     __syncwarp();
-                    if (box == 64) {                             // 128-byte rows, SWIZZLE_128B: piece j -> j ^ (row & 7)
+                    // 64-byte rows, SWIZZLE_64B: piece j -> j ^ ((row >> 1) & 3)
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 128 + ((j ^ (lane & 7)) << 4)),
-                                         "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
-                    } else {                                     // 64-byte rows, SWIZZLE_64B: piece j -> j ^ ((row >> 1) & 3)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)),
-                                         "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
-                    }
+                    for (int j = 0; j < 4; ++j)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)),
+                                     "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
                     tc::fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
@@ -545,9 +547,11 @@ struct MapKey {
     bool operator<(const MapKey& o) const { return std::tie(p, d0, d1, ld, b0, b1) < std::tie(o.p, o.d0, o.d1, o.ld, o.b0, o.b1); }
 };
 
-// row-major bf16 [rows, inner] with a row pitch of `ld` elements (0 = dense)
+}  // namespace
+
+// row-major bf16 [rows, inner] with a row pitch of `ld` elements (0 = dense)  (also used by gemm_chain.cu)
 int cached_map_2d(const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows, CUtensorMap* out,
-                  uint64_t ld = 0)
+                  uint64_t ld)
 {
     static std::map<MapKey, CUtensorMap> cache;
     static std::mutex mu;
@@ -586,6 +590,8 @@ int cached_map_out(const void* base, uint64_t cols, uint64_t rows, uint64_t bloc
     *out = it->second;
     return 0;
 }
+
+namespace {
 
 // head-major output map for c_tma == 3: dims {32 channels, rows, heads = BN/32, n-blocks}, box {32, 32, 1, 1}
 int cached_map_out_heads(const void* base, uint64_t rows, uint64_t heads, uint64_t blocks, CUtensorMap* out)
@@ -644,7 +650,7 @@ int build_prob(GemmProb& P, int& smem, const bf16* A, const bf16* A2, int K1, co
     int per_n = ctas / n_tiles;
     if (per_n > m_tiles) per_n = m_tiles;                        // (row ranges are dealt in 32-row blocks: >= 1 per CTA)
     OCC_CHECK(per_n >= 1, "gemm_tc: fewer CTAs than n-blocks");
-    P.bias = bias; P.residual = residual; P.C = C;
+    P.bias = bias; P.residual = residual; P.C = C; P.res_t32 = nullptr;
     P.ldc = blocked_out ? (long long)p.BN : (long long)N;
     P.nblk_stride = blocked_out ? (long long)M * p.BN : (long long)p.BN;
     P.stg_bytes = stg_bytes; P.M = M; P.N = N; P.BN = p.BN; P.nk = K / BLOCK_K; P.nk1 = K1 / BLOCK_K; P.act = act;
@@ -767,14 +773,14 @@ int gemm_tc_ln(const bf16* A, const bf16* W, const float* bias, const float* res
 //   value problems: Cv[i] = Av[i].Wv^T + bv (bf16, [M,256], TMA-store epilogue), i < nv <= 2  (TSA value_proj of each queue entry)
 //   projection    : Cq = [Aq | Aq2].Wq^T + bq (+ rq, fp32 [M,Nq]) as fp16                  (sampling offsets + attention logits)
 int gemm_tc_tsa_inputs(const bf16* const* Av, int nv, const bf16* Wv, const float* bv, bf16* const* Cv, const bf16* Aq,
-                       const bf16* Aq2, int K1q, const bf16* Wq, const float* bq, const float* rq, __half* Cq, int M, int Nq,
-                       int Kq, cudaStream_t stream)
+                       const bf16* Aq2, int K1q, const bf16* Wq, const float* bq, const float* rq, const float* rq_t32, __half* Cq,
+                       int M, int Nq, int Kq, cudaStream_t stream)
 {
     OCC_CHECK(nv >= 1 && nv <= 2, "gemm_tc_tsa_inputs: 1 or 2 value problems");
     const int num_sms = sm_count_current_device();
     const double wv = 256.0 * 256.0, wq = (double)Nq * Kq, tot = nv * wv + wq;
     int cq = (int)(num_sms * wq / tot + 0.5);
-    const int nq_tiles = Nq / make_plan(Nq, Kq, false, rq ? 4096 : 2048).BN;
+    const int nq_tiles = Nq / make_plan(Nq, Kq, false, (rq && !rq_t32) ? 4096 : 2048).BN;
     if (cq < nq_tiles) cq = nq_tiles;
     const int cv = (num_sms - cq) / nv;
     OCC_CHECK(cv >= 1, "gemm_tc_tsa_inputs: not enough SMs");
@@ -788,9 +794,17 @@ int gemm_tc_tsa_inputs(const bf16* const* Av, int nv, const bf16* Wv, const floa
         smem = sm > smem ? sm : smem;
     }
     // (built through the bf16 instantiation: out_half selects the fp16 packing at run time)
-    if (build_prob<bf16, false>(probs.p[nv], sm, Aq, Aq2, K1q, Wq, bq, rq, reinterpret_cast<bf16*>(Cq), M, Nq, Kq, ACT_NONE, false,
-                                0, 0, false, cq, begin)) return 1;
+    // rq_t32: the epilogue constant in the T32 layout -> the projection leaves through the TMA-store epilogue as well (the
+    // row-major fp32 `rq` forces the staged per-lane epilogue: 4.2-5.5 us per tile instead of 2.1, in-kernel timeline r2 call 8)
+    static const bool no_tma_store = getenv("OCC_GEMM_NO_TMA_STORE") != nullptr;
+    const bool t32 = rq_t32 != nullptr && !no_tma_store && M % 32 == 0;
+    if (build_prob<bf16, false>(probs.p[nv], sm, Aq, Aq2, K1q, Wq, bq, t32 ? nullptr : rq, reinterpret_cast<bf16*>(Cq), M, Nq, Kq,
+                                ACT_NONE, false, 0, 0, false, cq, begin)) return 1;
     probs.p[nv].out_half = 1;
+    if (t32) {
+        OCC_CHECK(probs.p[nv].c_tma == 1 && probs.p[nv].stg_bytes == 2048, "gemm_tc_tsa_inputs: T32 constant needs the 32-column TMA-store epilogue");
+        probs.p[nv].res_t32 = rq_t32;
+    }
     smem = sm > smem ? sm : smem;
     return launch_probs<bf16, false>(probs, smem, LnArgs{}, stream);
 }

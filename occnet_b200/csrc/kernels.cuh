@@ -67,7 +67,7 @@ template <typename T>
 int launch_prepare_query(const float* bev_queries, const float* pos, int64_t n, float* q_f32, T* q_t, T* q_pos_t,
                          int tiled, cudaStream_t stream);
 // row-major [rows,256] fp32 <-> "T32" block layout of the tensor-core path's residual stream (see elementwise.cu)
-int launch_t32_convert(const float* src, float* dst, int64_t rows, int untile, cudaStream_t stream);
+int launch_t32_convert(const float* src, float* dst, int64_t rows, int untile, cudaStream_t stream, int ncols = 256);
 // pos[q, :] = cat(col_embed[q % W], row_embed[q / W])     (mmdet LearnedPositionalEncoding)
 int launch_bev_pos(const float* row_embed, const float* col_embed, int bev_h, int bev_w, int half, float* pos,
                    cudaStream_t stream);

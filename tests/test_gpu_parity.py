@@ -504,7 +504,7 @@ def test_full_size_properties_bf16(tc):
         assert torch.equal(a[k], b[k]), f'{k} not deterministic'
     assert torch.equal(a['occ'].argmax(-1).to(torch.uint8), a['occ_cls'])
     assert torch.isfinite(a['bev_embed']).all() and torch.isfinite(a['occ']).all()
-    assert eng.launches_per_frame > 20
+    assert eng.launches_per_frame >= 10                         # every launch of the frame is one of the library's own kernels
     if tc:
         ref = engine_for(cfg, params, metas, 'bf16', tc=False).forward(fd, want=('bev_embed', 'occ', 'occ_cls', 'flow'))
         assert (a['bev_embed'] - ref['bev_embed']).abs().max().item() < 8e-2       # bf16 weights vs fp32 weights
@@ -745,7 +745,7 @@ for pb in (None, prev):
     ob = b.forward(fd, prev_bev=pb); lb = b.launches_per_frame
     for k in oa:
         assert torch.equal(oa[k], ob[k]), k
-    assert (lb - la) == (4 if pb is None else 0), (la, lb)
+    assert (lb - la) == (2 if pb is None else 0), (la, lb)       # layer 0: merged input GEMMs + gather (the LN chain replaces the lone SCA projection)
 print('OK')
 """
     assert 'OK' in _run_isolated(code)
