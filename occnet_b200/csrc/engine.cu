@@ -66,6 +66,7 @@ struct occb200_engine {
     ScaParams sp;
     bool cameras_set = false, finalized = false, taps = false;
     bool value_head_major = false;      // SCA value maps as [layer][head][token][32] (pair-fetch gather) instead of [layer][token][256]
+    bool gemm_chain = false;            // OCC_GEMM_CHAIN=1 at finalize: chained dense layers (gemm_chain.cu)
     DevBuf sca_sched;                   // scheduler words of the SM-tiled gather kernel (zeroed by every launch)
     DevBuf rot_map;                     // occb200_engine_set_prev_rotation: source row of every BEV cell (int32, -1 = outside)
     bool rot_set = false;
@@ -317,11 +318,12 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
         if (gemm_tc_blocked256((const bf16*)tokens, e->sca_v_all_wh.as<bf16>(), e->sca_v_all_b.as<float>(),
                                e->sca_value_all.as<bf16>(), ncam * Nv, c.num_layers * C, C, st, e->value_head_major)) return 2;
     }
-    // Chained dense layers (gemm_chain.cu): [TSA output_proj+LN -> SCA sampling projection] and [SCA output_proj+LN -> FFN1 ->
-    // FFN2+LN -> next layer's TSA value / sampling projections] are ONE persistent launch each (OCC_GEMM_CHAIN=0: one launch
-    // per layer, gemm_tc.cu)
-    static const bool chain_env = getenv("OCC_GEMM_CHAIN") == nullptr || atoi(getenv("OCC_GEMM_CHAIN")) != 0;
-    const bool use_chain = sizeof(T) == 2 && fuse_ln && q_half && chain_env && mode == MODE_FRAME && !e->value_head_major;
+    // Chained dense layers (gemm_chain.cu, OCC_GEMM_CHAIN=1): [TSA output_proj+LN -> SCA sampling projection] and [SCA
+    // output_proj+LN -> FFN1 -> FFN2+LN -> next layer's TSA value / sampling projections] as ONE persistent launch each: 30 launches
+    // per frame instead of 52 (13 dense-layer launches), bit-identical outputs -- and MEASURED 3 % SLOWER per frame (2.94 vs 2.86 ms,
+    // r2 call 11): every (op, n-block) switch inside the kernel re-pays the 128 KB weight load that a fresh launch pays, and the
+    // per-tile epilogues were already the bound.  Off by default.
+    const bool use_chain = sizeof(T) == 2 && fuse_ln && q_half && e->gemm_chain && mode == MODE_FRAME && !e->value_head_major;
     static const bool tsa_merge_env0 = getenv("OCC_TSA_MERGE") == nullptr || atoi(getenv("OCC_TSA_MERGE")) != 0;
     const bool tsa_merge_ok = tsa_merge_env0;
     bool tsa_inputs_done = false;           // this layer's TSA value / sampling projections were written by the previous chain
@@ -922,6 +924,7 @@ int occb200_engine_finalize(occb200_engine* e)
     }
     e->host_params.clear();
     e->l0_ready = false;
+    e->gemm_chain = getenv("OCC_GEMM_CHAIN") != nullptr && atoi(getenv("OCC_GEMM_CHAIN")) != 0;
     if (tc && e->qc_f32.p != nullptr && getenv("OCC_NO_L0_FOLD") == nullptr) {
         // Layer 0's TemporalSelfAttention (value_proj, query projection over [bev_queries | pos], gather, output_proj) and
         // its LayerNorm depend on parameters only when prev_bev is None: run the frame path's own kernels once, here.
