@@ -606,7 +606,7 @@ def run_backbone_leg(args, cfg, eng, dev, want):
                 'backbone_tensor_frac': round(gflop / bb_ms / pk['tf_sust'], 4),
                 'handover': 'bf16 channels-last levels written by the FPN convolutions, packed by the engine without a '
                             'transpose' if cl else 'fp32 NCHW levels',
-                'implicit_gemm': bool(os.environ.get('OCC_BACKBONE_IMPLICIT'))}
+                'implicit_gemm': os.environ.get('OCC_BACKBONE_IMPLICIT', '1') != '0'}
     except Exception as e:                                            # noqa: BLE001
         return {'error': f'{type(e).__name__}: {e}'[:300]}
 

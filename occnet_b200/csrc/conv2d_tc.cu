@@ -4,9 +4,8 @@
 // Used for the 3x3 convolutions of ResNet-50 / FPN and (KH = KW = 1) for the bottleneck's last 1x1 convolution with the
 // residual add + ReLU fused (reference: mmdet ResNet / FPN as configured in bevformer_base_occ.py:48-66).
 //
-// STATUS: second-step kernel of the backbone, written after the round-1 GPU budget was spent: builds for sm_100a,
-// NOT yet run on a GPU.  Opt-in (OCC_BACKBONE_IMPLICIT=1 inside the opt-in backbone engine); the default backbone
-// path uses explicit im2col + the validated gemm_tc kernel.
+// STATUS: validated on B200 in round 2 (tests/test_backbone_gpu.py with and without it; images -> voxels 75.9 -> 98.9 samples/s);
+// default for the stride-1 convolutions of the backbone (OCC_BACKBONE_IMPLICIT=0: explicit im2col + gemm_tc for everything).
 //
 // Same skeleton as gemm_tc.cu (persistent, one CTA per SM, warp-specialised), with im2col done by TMA as in conv3d_tc.cu:
 //   M tile  = 128 output pixels = 8 rows x 16 columns of one image; K loop = taps x (Cin / 64)

@@ -1,7 +1,8 @@
 """Parity of the image backbone + neck (ResNet-50 + FPN) against its oracle (oracle/backbone.py, pinned
 bit-exactly to torchvision's resnet50 / FeaturePyramidNetwork), and of the channels-last bf16 hand-over to the hot path.
 
-    OCC_BACKBONE_IMPLICIT=1 python -m pytest tests/test_backbone_gpu.py -q -k tcgen05     # + conv2d_tc.cu (TMA im2col)
+The stride-1 convolutions run on the TMA-im2col implicit-GEMM kernel (conv2d_tc.cu) by default; `test_backbone_bf16_tcgen05_explicit_im2col`
+covers the explicit im2col + gemm_tc path (OCC_BACKBONE_IMPLICIT=0) in a child process (the switch is read once per process).
 """
 import os
 import sys
@@ -40,6 +41,15 @@ def test_backbone_bf16_simt_close_to_oracle():
 def test_backbone_bf16_tcgen05_close_to_oracle():
     err, mag = _run('bf16', True)
     assert max(e / max(m, 1.0) for e, m in zip(err, mag)) < 8e-2, (err, mag)
+
+
+def test_backbone_bf16_tcgen05_explicit_im2col():
+    import subprocess
+    code = ("import sys; sys.path.insert(0, 'tests'); import test_backbone_gpu as t; "
+            "err, mag = t._run('bf16', True); assert max(e / max(m, 1.0) for e, m in zip(err, mag)) < 8e-2, (err, mag); print('OK')")
+    r = subprocess.run([sys.executable, '-c', code], cwd=ROOT, env=dict(os.environ, OCC_BACKBONE_IMPLICIT='0'), capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and 'OK' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_backbone_odd_sizes_fp32():
