@@ -35,6 +35,45 @@ bev_to_voxel_kernel(const float* __restrict__ bev, int bev_h, int bev_w, int Z, 
     store8(vox + ((int64_t)x * bev_h + y) * 256 + lane * 8, o);
 }
 
+// The same lift straight from the T32 residual-stream layout of the tensor-core path (Z = mid = 16), bf16 out: one CTA = one
+// 32-row block.  Thread (lane = row, warp = (z block of 4, cm block of 8)) reads the 8 float4 {cm, z0..z0+3} of its row -- 512
+// contiguous bytes per warp instruction in T32 -- and owns a 4 (z) x 8 (cm) block of the output row; rows are staged in shared
+// memory (528-byte pitch) and leave as whole 512-byte voxel columns.  Replaces t32_convert + bev_to_voxel when bev_embed itself
+// is not requested.
+__global__ void __launch_bounds__(256)
+t32_to_voxel_kernel(const float* __restrict__ bev_t32, int bev_h, int bev_w, bf16* __restrict__ vox)
+{
+    __shared__ __align__(16) uint8_t rows[32 * 528];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int zb = warp & 3, cmb = warp >> 2;                   // z0 = 4 zb, cm0 = 8 cmb
+    const int Nq = bev_h * bev_w;
+    const int64_t R = blockIdx.x;
+    const float4* blk = reinterpret_cast<const float4*>(bev_t32) + R * 8 * 8 * 32 + lane;
+    float v[8][4];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = (cmb * 8 + k) * 16 + zb * 4;              // input channel of (cm, z0): cm * Z + z
+        const float4 t = __ldg(blk + ((c >> 5) * 8 + ((c & 31) >> 2)) * 32);
+        v[k][0] = t.x; v[k][1] = t.y; v[k][2] = t.z; v[k][3] = t.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                               // output channels (z0 + i) * 16 + cm0 .. + 7
+        const uint4 o = make_uint4(pack_bf16x2(v[0][i], v[1][i]), pack_bf16x2(v[2][i], v[3][i]), pack_bf16x2(v[4][i], v[5][i]),
+                                   pack_bf16x2(v[6][i], v[7][i]));
+        *reinterpret_cast<uint4*>(rows + lane * 528 + ((zb * 4 + i) * 16 + cmb * 8) * 2) = o;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                               // warp w writes rows w, w + 8, ...: 32 lanes x 16 B = one voxel column
+        const int r = warp + 8 * i;
+        const int64_t q = R * 32 + r;
+        if (q < Nq) {
+            const int x = (int)(q % bev_w), y = (int)(q / bev_w);
+            *reinterpret_cast<uint4*>(vox + ((int64_t)x * bev_h + y) * 256 + lane * 8) = *reinterpret_cast<const uint4*>(rows + r * 528 + lane * 16);
+        }
+    }
+}
+
 // one thread = one voxel x 32 output channels; block = 8 (y) x 16 (z) voxels at one x
 template <typename T, int CIN>
 __global__ void __launch_bounds__(128)
@@ -181,6 +220,12 @@ int launch_bev_to_voxel(const float* bev, int bev_h, int bev_w, int Z, int mid, 
 {
     OCC_CHECK(Z * mid == 256, "bev_to_voxel: embed_dims must be 256");
     bev_to_voxel_kernel<T><<<ceil_div((int64_t)bev_h * bev_w, 8), 256, 0, stream>>>(bev, bev_h, bev_w, Z, mid, vox);
+    OCC_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_t32_to_voxel(const float* bev_t32, int bev_h, int bev_w, bf16* vox, cudaStream_t stream)
+{
+    t32_to_voxel_kernel<<<ceil_div((int64_t)bev_h * bev_w, 32), 256, 0, stream>>>(bev_t32, bev_h, bev_w, vox);
     OCC_CUDA(cudaGetLastError());
     return 0;
 }

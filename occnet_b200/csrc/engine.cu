@@ -550,7 +550,10 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
             OCC_CUDA(cudaMemcpyAsync(e->tap_layer.as<float>() + (size_t)l * Nq * C, q_f32, (size_t)Nq * C * 4,
                                      cudaMemcpyDeviceToDevice, st));
     }
-    if (fuse_ln) {                                                 // back to row-major for the outputs / voxel decoder
+    const int X = c.bev_w, Y = c.bev_h, Z = c.pillar_h, mid = C / Z;
+    // the voxel lift reads the T32 residual stream directly when bev_embed itself is not an output (one kernel instead of two)
+    const bool lift_from_t32 = fuse_ln && sizeof(T) == 2 && bev_embed == nullptr && Z == 16 && mid == 16;
+    if (fuse_ln && !lift_from_t32) {                               // back to row-major for the outputs / voxel decoder
         ProfScope ps(e, st, CAT_PACK);
         if (launch_t32_convert(q_f32, x_f32, Nq, 1, st)) return 2;
         advance();
@@ -560,10 +563,11 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
         OCC_CUDA(cudaMemcpyAsync(bev_embed, q_f32, (size_t)Nq * C * 4, cudaMemcpyDeviceToDevice, st));
     if (!occ_logits && !flow && !cls_u8 && !cls_i64) return 0;
     // ---- voxel decoder + heads
-    const int X = c.bev_w, Y = c.bev_h, Z = c.pillar_h, mid = C / Z;
     {
         ProfScope ps(e, st, CAT_VOX);
-        if (launch_bev_to_voxel<T>(q_f32, c.bev_h, c.bev_w, Z, mid, e->vox0.as<T>(), st)) return 2;
+        if (lift_from_t32) {
+            if (launch_t32_to_voxel(q_f32, c.bev_h, c.bev_w, e->vox0.as<bf16>(), st)) return 2;
+        } else if (launch_bev_to_voxel<T>(q_f32, c.bev_h, c.bev_w, Z, mid, e->vox0.as<T>(), st)) return 2;
     }
     const bool conv_tc = sizeof(T) == 2 && c.use_tensor_cores && e->conv_wh[0].p && e->conv_wh[1].p && Z == 16;
     {

@@ -81,6 +81,8 @@ int launch_gather_rows(const float* src, const int32_t* map, int rows, int C, T*
 // bev [Nq = H*W, C = mid*Z] f32 -> vox [X=W][Y=H][Z][mid] T with vox[x][y][z][cm] = bev[y*W+x][cm*Z+z]
 template <typename T>
 int launch_bev_to_voxel(const float* bev, int bev_h, int bev_w, int Z, int mid, T* vox, cudaStream_t stream);
+// the same lift from the T32 layout of the residual stream (Z = mid = 16, rows padded to 32), bf16 voxels
+int launch_t32_to_voxel(const float* bev_t32, int bev_h, int bev_w, bf16* vox, cudaStream_t stream);
 // 3x3x3 conv (pad 1) + folded BatchNorm + ReLU on channels-last [X][Y][Z][Cin] -> [X][Y][Z][Cout=32]
 // wfold: [27][Cin][32] f32 (tap = (dz*3+dy)*3+dx), bfold: [32]
 template <typename T>

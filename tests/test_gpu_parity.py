@@ -726,6 +726,18 @@ def test_full_size_six_layers_bf16_temporal_prev_bev(golden_dir):
     _check_full6_bf16(True, golden_dir)
 
 
+def test_voxel_lift_from_t32_layout_is_bit_identical():
+    """When bev_embed is not requested the voxel lift reads the T32 residual stream directly (t32_to_voxel_kernel) instead of
+    untiling to row-major first: same values, same rounding -> bit-identical occupancy / flow."""
+    cfg, params, feats, metas, _ = make_case('small6')
+    eng = engine_for(cfg, params, metas, 'bf16', tc=True)
+    fd = [f[0].to(DEV) for f in feats]
+    a = {k: v.clone() for k, v in eng.forward(fd, want=('bev_embed', 'occ', 'flow', 'occ_cls')).items()}
+    b = eng.forward(fd, want=('occ', 'flow', 'occ_cls'))
+    for k in b:
+        assert torch.equal(a[k], b[k]), k
+
+
 def test_chained_dense_layers_are_bit_identical():
     """OCC_GEMM_CHAIN=1 (gemm_chain.cu: the dense layers between two gathers as ONE persistent launch, a CTA walking the op list
     over its own rows with per-tile completion counters) against one launch per layer (gemm_tc.cu): same MMA order, same epilogue
