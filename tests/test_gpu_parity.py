@@ -969,3 +969,32 @@ def test_plugin_ray_metrics_main_matches_oracle():
     pcd = rm.process_one_sample(sem_pred, rm.generate_lidar_rays(), fixtures.make_ray_origins(T=2), flow_pred, device=DEV)
     np.testing.assert_array_equal(pcd, ORM.process_one_sample(sem_pred, ORM.generate_lidar_rays(),
                                                               fixtures.make_ray_origins(T=2), flow_pred))
+
+
+def test_plugin_submission_writer_matches_reference_format(tmp_path):
+    """`datasets/submission.format_results` = the prediction half of the reference's `NuSceneOcc.format_results`
+    (nuscenes_occ.py:188-257): per token {pcd_cls int8, pcd_dist fp16, pcd_flow fp16} from `process_one_sample`, pickled into a
+    deterministic `submission.gz`.  Arrays must equal the oracle's restatement bit for bit."""
+    import gzip
+    import pickle
+    from projects.mmdet3d_plugin.datasets import submission as sub
+    _, _, ORM = _oracle()
+    sem_pred, flow_pred, _, _ = _metric_fixture()
+    origins = [fixtures.make_ray_origins(T=2), fixtures.make_ray_origins(T=3)]
+    results = [{'occ_results': torch.from_numpy(sem_pred.astype(np.int64)), 'flow_results': torch.from_numpy(flow_pred)},
+               {'occ_results': torch.from_numpy(sem_pred[::-1].copy().astype(np.int64)), 'flow_results': torch.from_numpy(flow_pred[::-1].copy())}]
+    out = sub.format_results(results, ['tok_a', 'tok_b'], origins, submission_prefix=str(tmp_path), device=DEV)
+    blob = open(os.path.join(str(tmp_path), 'submission.gz'), 'rb').read()
+    loaded = pickle.loads(gzip.decompress(blob))
+    assert set(loaded) == set(sub.SUBMISSION_META) | {'results'} and list(loaded['results']) == ['tok_a', 'tok_b']
+    rays = ORM.generate_lidar_rays()
+    for tok, res, orig in zip(('tok_a', 'tok_b'), results, origins):
+        want = ORM.process_one_sample(res['occ_results'].numpy(), rays, orig, res['flow_results'].numpy())
+        got = loaded['results'][tok]
+        assert got['pcd_cls'].dtype == np.int8 and got['pcd_dist'].dtype == np.float16 and got['pcd_flow'].dtype == np.float16
+        np.testing.assert_array_equal(got['pcd_cls'], want[:, 0].astype(np.int8))
+        np.testing.assert_array_equal(got['pcd_dist'], want[:, 1].astype(np.float16))
+        np.testing.assert_array_equal(got['pcd_flow'], want[:, 2:4].astype(np.float16))
+        np.testing.assert_array_equal(out['results'][tok]['pcd_dist'], got['pcd_dist'])
+    again = sub.format_results(results, ['tok_a', 'tok_b'], origins, submission_prefix=str(tmp_path), device=DEV)
+    assert open(os.path.join(str(tmp_path), 'submission.gz'), 'rb').read() == blob and again.keys() == out.keys()
