@@ -93,7 +93,7 @@ struct LnArgs {                                           // fused LayerNorm epi
 // ring only carries A tiles; otherwise each stage carries an A tile and a W k-block (v1 behaviour).
 constexpr int MAX_PROBS = 3;
 struct GemmProb {
-    CUtensorMap tmA, tmA2, tmW, tmC;
+    CUtensorMap tmA, tmA2, tmW, tmC, tmC2;                   // (LayerNorm launches: tmC = y_bf16, tmC2 = y_pos_bf16, [M,256] bf16)
     const float* bias; const float* residual; void* C;
     const float* res_t32;                                     // optional fp32 epilogue constant [M,N] in the T32 block layout
                                                               // (TMA-store path: the row-per-thread read is then coalesced)
@@ -114,6 +114,7 @@ gemm_tc_kernel(const __grid_constant__ GemmProbs probs, LnArgs ln, long long* __
     while (pi + 1 < probs.n && (int)blockIdx.x >= probs.p[pi + 1].cta_begin) ++pi;
     const GemmProb& P = probs.p[pi];
     const CUtensorMap& tmA = P.tmA; const CUtensorMap& tmA2 = P.tmA2; const CUtensorMap& tmW = P.tmW; const CUtensorMap& tmC = P.tmC;
+    const CUtensorMap& tmC2 = P.tmC2;
     const float* __restrict__ bias = P.bias;
     const float* __restrict__ residual = P.residual;
     const float* __restrict__ res_t32 = P.res_t32;
@@ -364,7 +365,13 @@ gemm_tc_kernel(const __grid_constant__ GemmProbs probs, LnArgs ln, long long* __
                     tc::tmem_ld_wait();
                     float4* yo = reinterpret_cast<float4*>(ln.y_f32) + blk4 + (size_t)(c0 >> 5) * 256;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {                // normalise my row: fp32 straight to T32, bf16 via staging
+                    // bf16 copies: my row -> swizzled staging ([32 rows x 64 B], SWIZZLE_64B: 16-byte piece p of row r at
+                    // p ^ ((r >> 1) & 3)) -> one TMA store per [32 x 32] block (was: staging + LDS + per-lane STG.128)
+                    if (lane == 0) tc::tma_store_wait_read();
+                    __syncwarp();
+                    const uint32_t srow = stg + lane * 64, swz = (lane >> 1) & 3;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {                // normalise my row: fp32 straight to T32
                         const float4 g = reinterpret_cast<const float4*>(cvec + 256 + c0)[j];
                         const float4 be = reinterpret_cast<const float4*>(cvec + 512 + c0)[j];
                         float4 y;
@@ -373,33 +380,21 @@ gemm_tc_kernel(const __grid_constant__ GemmProbs probs, LnArgs ln, long long* __
                         y.z = (__uint_as_float(r[4 * j + 2]) - mean) * rstd * g.z + be.z;
                         y.w = (__uint_as_float(r[4 * j + 3]) - mean) * rstd * g.w + be.w;
                         if (ln.y_f32) yo[j * 32] = y;
-                        // staging block: bytes [0,2K) = y as bf16 rows of 64 B, [2K,4K) = (y + pos) as bf16
-                        reinterpret_cast<uint2*>(stg4)[lane * 8 + (j ^ (lane & 7))] =
-                            make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+                        const uint32_t dst = srow + ((((uint32_t)j >> 1) ^ swz) << 4) + (j & 1) * 8;
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(pack_bf16x2(y.x, y.y)), "r"(pack_bf16x2(y.z, y.w)) : "memory");
                         if (ln.y_pos_bf16) {
                             const float4 p4 = nxt[j];
-                            reinterpret_cast<uint2*>(stg4)[256 + lane * 8 + (j ^ (lane & 7))] =
-                                make_uint2(pack_bf16x2(y.x + p4.x, y.y + p4.y), pack_bf16x2(y.z + p4.z, y.w + p4.w));
+                            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + 2048), "r"(pack_bf16x2(y.x + p4.x, y.y + p4.y)),
+                                         "r"(pack_bf16x2(y.z + p4.z, y.w + p4.w)) : "memory");
                         }
                     }
-                    __syncwarp();
                     if (ln.y_pos_bf16 && ci + 1 < 4) t32_load(ln.pos, c0 + 32, nxt);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {                // coalesced bf16 stores: 8 rows x 64 B per instruction
-                        const int rr = 8 * i + (lane >> 2), grow = row0 + rr, pc = lane & 3;   // 16-byte piece pc = cols 8pc..8pc+7
-                        if (grow < M) {
-                            const size_t o = (size_t)grow * 256 + c0 + pc * 8;
-                            const uint2 a = reinterpret_cast<uint2*>(stg4)[rr * 8 + ((2 * pc) ^ (rr & 7))];
-                            const uint2 b = reinterpret_cast<uint2*>(stg4)[rr * 8 + ((2 * pc + 1) ^ (rr & 7))];
-                            if (ln.y_bf16) *reinterpret_cast<uint4*>(ln.y_bf16 + o) = make_uint4(a.x, a.y, b.x, b.y);
-                            if (ln.y_pos_bf16) {
-                                const uint2 c = reinterpret_cast<uint2*>(stg4)[256 + rr * 8 + ((2 * pc) ^ (rr & 7))];
-                                const uint2 d = reinterpret_cast<uint2*>(stg4)[256 + rr * 8 + ((2 * pc + 1) ^ (rr & 7))];
-                                *reinterpret_cast<uint4*>(ln.y_pos_bf16 + o) = make_uint4(c.x, c.y, d.x, d.y);
-                            }
-                        }
-                    }
+                    tc::fence_proxy_async_smem();
                     __syncwarp();
+                    if (lane == 0) {
+                        if (ln.y_bf16) { tc::tma_store_3d(&tmC, stg, c0, row0, 0); tc::tma_store_commit(); }
+                        if (ln.y_pos_bf16) { tc::tma_store_3d(&tmC2, stg + 2048, c0, row0, 0); tc::tma_store_commit(); }
+                    }
                 }
             } else if (sizeof(TC) == 2 && c_tma != 0) {
                 // 16-bit outputs: accumulator row -> bias/act -> packed 16-bit -> swizzled staging rows -> ONE TMA store
@@ -499,7 +494,7 @@ gemm_tc_kernel(const __grid_constant__ GemmProbs probs, LnArgs ln, long long* __
             if (++as == 2) { as = 0; aph ^= 1; }
         }
     }
-    if (c_tma != 0 && warp >= 2 && lane == 0) tc::tma_store_wait_all();   // output stores performed before the grid completes
+    if ((LN || c_tma != 0) && warp >= 2 && lane == 0) tc::tma_store_wait_all();   // output stores performed before the grid completes
     tc::tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) stamp(15);
@@ -630,7 +625,7 @@ int build_prob(GemmProb& P, int& smem, const bf16* A, const bf16* A2, int K1, co
     if (A2) { if (cached_map_2d(A2, (uint64_t)(K - K1), (uint64_t)M, BLOCK_K, BLOCK_M, &P.tmA2, (uint64_t)lda2)) return 1; }
     else P.tmA2 = P.tmA;
     if (cached_map_2d(W, (uint64_t)K, (uint64_t)N, BLOCK_K, (uint32_t)p.BN, &P.tmW)) return 1;
-    P.tmC = P.tmW;
+    P.tmC = P.tmW; P.tmC2 = P.tmW;
     P.c_tma = 0;
     if (use_tma_store) {
         const uint32_t box_cols = 32u;
@@ -765,8 +760,16 @@ int gemm_tc_ln(const bf16* A, const bf16* W, const float* bias, const float* res
 {
     OCC_CHECK(bias && residual && gamma && beta, "gemm_tc_ln: bias, residual, gamma, beta are required");
     OCC_CHECK(y_pos_bf16 == nullptr || pos != nullptr, "gemm_tc_ln: pos required for y_pos");
-    return launch<float, true>(A, nullptr, 0, W, bias, residual, (float*)nullptr, LnArgs{gamma, beta, pos, y_f32, y_bf16, y_pos_bf16},
-                               M, 256, K, ACT_NONE, stream);
+    GemmProbs probs;
+    probs.n = 1;
+    int smem = 0;
+    if (build_prob<float, true>(probs.p[0], smem, A, nullptr, 0, W, bias, residual, (float*)nullptr, M, 256, K, ACT_NONE, false, 0, 0, false,
+                                0, 0)) return 1;
+    // the bf16 copies of the LayerNorm output leave through TMA stores of [32 rows x 32 columns]
+    probs.p[0].tmC2 = probs.p[0].tmC;
+    if (y_bf16 && cached_map_out(y_bf16, 256, (uint64_t)M, 1, 32u, &probs.p[0].tmC)) return 1;
+    if (y_pos_bf16 && cached_map_out(y_pos_bf16, 256, (uint64_t)M, 1, 32u, &probs.p[0].tmC2)) return 1;
+    return launch_probs<float, true>(probs, smem, LnArgs{gamma, beta, pos, y_f32, y_bf16, y_pos_bf16}, stream);
 }
 
 // Two (or three) independent 16-bit-output GEMMs in ONE launch: the CTAs are shared out in proportion to N.K.
