@@ -103,7 +103,10 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        // all 32 lanes run the issue loop in warp-uniform control flow (operands in the uniform datapath); elect.sync picks the
+        // issuing lane -- see tc::umma_bf16_elect (the N = 64 / 128 layers of the backbone are MMA-issue bound)
+        tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+        {
             const uint32_t idesc = tc::make_idesc_bf16(BLOCK_M, BN);
             int s = 0; uint32_t ph = 0; int as = 0; uint32_t aph = 0;
             for (int t = t_begin; t < t_end; ++t) {
@@ -117,9 +120,10 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
                     const uint64_t db = tc::make_smem_desc(a_addr + A_TILE_BYTES, 128);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / 16; ++k)
-                        tc::umma_bf16(tmem_base + as * 256, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                    tc::umma_commit(empty_bar(s));
-                    if (kb == nk - 1) tc::umma_commit(tfull_bar(as));
+                        tc::umma_bf16_elect(tmem_base + as * 256, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    tc::umma_commit_elect(empty_bar(s));
+                    tc::umma_commit_elect(tfull_bar(as), kb == nk - 1 ? 1u : 0u);
+                    __syncwarp();
                     if (++s == stages) { s = 0; ph ^= 1; }
                 }
                 if (++as == 2) { as = 0; aph ^= 1; }

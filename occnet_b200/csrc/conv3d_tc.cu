@@ -116,6 +116,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
             const uint64_t da0 = tc::make_smem_desc(a_base, ROW_BYTES), db0 = tc::make_smem_desc(w_base, ROW_BYTES);
             int s = 0; uint32_t ph = 0;
             int n_base = 0;
+            if (UNI) tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);     // (a broadcast from lane 0 is a uniform value to ptxas)
             tc::mbar_wait(w_bar, 0);
             tc::tc_fence_after();
             for (int t = t_begin; t < t_end;) {
@@ -139,7 +140,24 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
                     for (int dz = 0; dz < 3; ++dz) {
                         tc::mbar_wait(full_bar(s), ph);
                         tc::tc_fence_after();
-                        if (leader) {
+                        if constexpr (UNI) {
+                            // warp-uniform control flow: operands stay in the uniform datapath, elect.sync issues from one lane
+                            const uint32_t desc_hi = (uint32_t)(da0 >> 32);                    // == high word of db0 (same ROW_BYTES)
+                            const uint32_t a_s = (uint32_t)da0 + (uint32_t)((s * A_BYTES) >> 4);
+                            const uint32_t b_z = (uint32_t)db0 + (uint32_t)(((dz * 9 + off) * W_TAP_BYTES) >> 4);
+                            const uint32_t wrap = first < cnt ? 1u : 0u, b_wrap = (uint32_t)((first * W_TAP_BYTES) >> 4);
+#pragma unroll
+                            for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+                                for (int k = 0; k < CIN / 16; ++k) {
+                                    const uint32_t a_lo = a_s + (uint32_t)((dy * DY_BYTES) >> 4) + 2 * k;
+                                    const uint32_t b_lo = b_z + (uint32_t)((dy * 3 * W_TAP_BYTES) >> 4) + 2 * k;
+                                    tc::umma_bf16_acc_elect_lo(d0, a_lo, b_lo, desc_hi, i_first);
+                                    tc::umma_bf16_acc_elect_lo(tmem_base, a_lo, b_lo + b_wrap, desc_hi, i_rest, wrap);
+                                }
+                            }
+                            tc::umma_commit_elect(empty_bar(s));
+                        } else if (leader) {
 #pragma unroll
                             for (int dy = 0; dy < 3; ++dy) {
                                 const int t9 = dz * 3 + dy;
@@ -160,7 +178,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
                     // outputs whose last plane this was: x = p-1 (and x = X-1 on the last plane)
                     for (int x = x_lo; x <= x_hi; ++x) {
                         if (min(x + 1, X - 1) != p) continue;
-                        if (leader) tc::umma_commit(tfull_bar((n_base + (x - xa)) & (SLOTS - 1)));
+                        if constexpr (UNI) tc::umma_commit_elect(tfull_bar((n_base + (x - xa)) & (SLOTS - 1)));
+                        else if (leader) tc::umma_commit(tfull_bar((n_base + (x - xa)) & (SLOTS - 1)));
                     }
                 }
                 n_base += xb - xa;

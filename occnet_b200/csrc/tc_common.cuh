@@ -114,6 +114,51 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// The same MMA issued from warp-uniform control flow: every lane executes the statement, `elect.sync` picks the one lane that
+// issues.  With the C++ form `if (lane == 0) umma_bf16(...)` the operands are computed inside a divergent region, where ptxas may
+// not use the uniform datapath: every tcgen05.mma was preceded by an ELECT + 7 x R2UR.BROADCAST waterfall loop (~21 instructions
+// per MMA on the single issuing warp -- the limiter of the conv3d kernel).  Requires all 32 lanes converged.
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
+                                                uint32_t enable = 1u)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, q, e;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 e, %5, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "and.pred q, q, e;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(enable)
+        : "memory");
+}
+// Same, for the issue-bound small-N MMAs of the conv kernel: both descriptors share one constant high word (layout, version, SBO)
+// and differ only in the 14-bit address field, so the caller passes the LOW words and the per-MMA address update is one 32-bit add
+// + one R2UR per operand instead of a 64-bit add + two; the MMA always accumulates.
+__device__ __forceinline__ void umma_bf16_acc_elect_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                                       uint32_t enable = 1u)
+{
+    asm volatile(
+        "{\n\t.reg .pred q, e;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 e, %5, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "and.pred q, q, e;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, 1;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(enable)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar, uint32_t enable = 1u)
+{
+    asm volatile(
+        "{\n\t.reg .pred q, e;\n\t"
+        "setp.ne.b32 e, %1, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "and.pred q, q, e;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(bar), "r"(enable)
+        : "memory");
+}
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
