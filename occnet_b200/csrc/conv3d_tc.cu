@@ -146,16 +146,29 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
                             const uint32_t a_s = (uint32_t)da0 + (uint32_t)((s * A_BYTES) >> 4);
                             const uint32_t b_z = (uint32_t)db0 + (uint32_t)(((dz * 9 + off) * W_TAP_BYTES) >> 4);
                             const uint32_t wrap = first < cnt ? 1u : 0u, b_wrap = (uint32_t)((first * W_TAP_BYTES) >> 4);
+                            // one (warp-uniform) branch per STAGE: the 3-output window wraps around the TMEM slot ring for 2 of 8
+                            // positions only, and the second MMA's operand set-up costs as much as the first's
+                            if (!wrap) {
 #pragma unroll
-                            for (int dy = 0; dy < 3; ++dy) {
+                                for (int dy = 0; dy < 3; ++dy) {
 #pragma unroll
-                                for (int k = 0; k < CIN / 16; ++k) {
-                                    const uint32_t a_lo = a_s + (uint32_t)((dy * DY_BYTES) >> 4) + 2 * k;
-                                    const uint32_t b_lo = b_z + (uint32_t)((dy * 3 * W_TAP_BYTES) >> 4) + 2 * k;
-                                    tc::umma_bf16_acc_elect_lo(d0, a_lo, b_lo, desc_hi, i_first);
-                                    tc::umma_bf16_acc_elect_lo(tmem_base, a_lo, b_lo + b_wrap, desc_hi, i_rest, wrap);
+                                    for (int k = 0; k < CIN / 16; ++k)
+                                        tc::umma_bf16_acc_elect_lo(d0, a_s + (uint32_t)((dy * DY_BYTES) >> 4) + 2 * k,
+                                                                   b_z + (uint32_t)((dy * 3 * W_TAP_BYTES) >> 4) + 2 * k, desc_hi, i_first);
+                                }
+                            } else {
+#pragma unroll
+                                for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+                                    for (int k = 0; k < CIN / 16; ++k) {
+                                        const uint32_t a_lo = a_s + (uint32_t)((dy * DY_BYTES) >> 4) + 2 * k;
+                                        const uint32_t b_lo = b_z + (uint32_t)((dy * 3 * W_TAP_BYTES) >> 4) + 2 * k;
+                                        tc::umma_bf16_acc_elect_lo(d0, a_lo, b_lo, desc_hi, i_first);
+                                        tc::umma_bf16_acc_elect_lo(tmem_base, a_lo, b_lo + b_wrap, desc_hi, i_rest);
+                                    }
                                 }
                             }
+                            __syncwarp();
                             tc::umma_commit_elect(empty_bar(s));
                         } else if (leader) {
 #pragma unroll
