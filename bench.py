@@ -385,6 +385,10 @@ def run_ours(args):
                     peak=pk['hbm'], unit='GB/s', frac=r['frac'], peak_source=pk['source'] + ' (copy bandwidth)',
                     algorithmic_bytes_per_launch=int(r['algorithmic_bytes_per_frame'] / n_l),
                     l1_bytes_per_clk_per_sm=r.get('l1_bytes_per_clk_per_sm'))
+    if dom == 'sca_gather':
+        roof['algorithmic_bytes_note'] = ('operator boundary as launched: value maps 6*Nv*256*s + fp16 offsets/logits Nq*768*2 + output '
+                                          'Nq*256*s (SURVEY 8(d) quotes 166 MB/layer for a kernel that never materialises offsets/logits); '
+                                          'the kernel is bound by the L1/LSU data path (l1_bytes_per_clk_per_sm), not by HBM: DESIGN.md section 4')
     roof.update(traffic=tr.get('dram_bytes_per_launch') if tr else None, traffic_source=traffic.get('_source'),
                 avg_launch_ms=round(r['ms_per_frame'] / n_l, 4), launches_per_frame=n_l)
     cpu = cpu_baseline(cfg) if (world == 1 and not args.no_cpu) else None
