@@ -41,10 +41,14 @@ constexpr int BAR_BYTES = 512;
 // instructions): loop counters, stage indices and UMMA descriptors are then warp-uniform values the compiler keeps in the
 // uniform datapath, instead of per-lane registers that need an R2UR move in front of every tcgen05.mma operand (ncu of the
 // single-lane version: 1.8 M R2UR + 1.3 M IMAD around 0.19 M MMAs; the issuing thread, not the tensor pipe, was the limiter).
-template <int CIN, bool UNI>
+// EPI: 0 = bf16 out = relu(acc + bias) (the bf16 configuration); fp32-storage configuration, one of three split passes
+// (hi.W_hi, lo.W_hi, hi.W_lo of the bf16 split of an fp32 input, relative error ~2^-16 like gemm_tc_split3):
+// 1 = out_f32 = acc, 2 = out_f32 += acc, 3 = out_f32 = relu(out_f32 + acc + bias).  Every output row is owned by one thread per
+// pass, so the fp32 accumulation across passes needs no atomics.
+template <int CIN, bool UNI, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
-                 const float* __restrict__ bias, bf16* __restrict__ out, int X, int Y)
+                 const float* __restrict__ bias, bf16* __restrict__ out, float* __restrict__ out_f32, int X, int Y)
 {
     constexpr int ROW_BYTES = CIN * 2;                       // 32 (SWIZZLE_32B) or 64 (SWIZZLE_64B)
     constexpr int A_BYTES = HALO_ROWS * ROW_BYTES;           // 5 / 10 KB per stage (three dy sub-views of 128 rows)
@@ -230,16 +234,31 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
             const int row = quarter * 32 + lane;
             const int y = y0 + row / TILE_Z, z = row % TILE_Z;
             if (y < Y) {
-                uint4* op = reinterpret_cast<uint4*>(out + ((((size_t)x * Y + y) * TILE_Z + z) * COUT));
+                if constexpr (EPI == 0) {
+                    uint4* op = reinterpret_cast<uint4*>(out + ((((size_t)x * Y + y) * TILE_Z + z) * COUT));
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float v[8];
+                    for (int i = 0; i < 4; ++i) {
+                        float v[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(r[8 * i + j]) + b[8 * i + j], 0.f);
-                    uint4 u;
-                    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
-                    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
-                    op[i] = u;
+                        for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(r[8 * i + j]) + b[8 * i + j], 0.f);
+                        uint4 u;
+                        u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+                        u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+                        op[i] = u;
+                    }
+                } else {
+                    float4* op = reinterpret_cast<float4*>(out_f32 + ((((size_t)x * Y + y) * TILE_Z + z) * COUT));
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float4 a = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                                               __uint_as_float(r[4 * i + 3]));
+                        if constexpr (EPI >= 2) { const float4 q = op[i]; a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w; }
+                        if constexpr (EPI == 3) {
+                            a.x = fmaxf(a.x + b[4 * i], 0.f); a.y = fmaxf(a.y + b[4 * i + 1], 0.f);
+                            a.z = fmaxf(a.z + b[4 * i + 2], 0.f); a.w = fmaxf(a.w + b[4 * i + 3], 0.f);
+                        }
+                        op[i] = a;
+                    }
                 }
             }
         }
@@ -254,15 +273,18 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
 
 }  // namespace
 
-int launch_conv3d_tc(const bf16* in, const bf16* w_tap_major, const float* bias, int X, int Y, int Z, int Cin,
-                     bf16* out, cudaStream_t stream)
+namespace {
+// in_pitch: elements between consecutive voxels of `in` (Cin for a dense tensor, 2*Cin for one half of a [hi | lo] split)
+template <int EPI>
+int launch_conv3d_tc_impl(const bf16* in, int in_pitch, const bf16* w_tap_major, const float* bias, int X, int Y, int Z, int Cin,
+                          bf16* out, float* out_f32, cudaStream_t stream)
 {
     OCC_CHECK(Z == TILE_Z && (Cin == 16 || Cin == 32), "conv3d_tc: Z must be 16 and Cin in {16, 32}");
     const int row_bytes = Cin * 2;
     CUtensorMap tmIn, tmW;
     {
         const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Z, (uint64_t)Y, (uint64_t)X};
-        const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)Z * Cin * 2, (uint64_t)Y * Z * Cin * 2};
+        const uint64_t strides[3] = {(uint64_t)in_pitch * 2, (uint64_t)Z * in_pitch * 2, (uint64_t)Y * Z * in_pitch * 2};
         const uint32_t box[4] = {(uint32_t)Cin, (uint32_t)TILE_Z, (uint32_t)(TILE_Y + 2), 1u};
         if (make_tensor_map_bf16(&tmIn, in, 4, dims, strides, box, row_bytes)) return 1;
     }
@@ -277,17 +299,39 @@ int launch_conv3d_tc(const bf16* in, const bf16* w_tap_major, const float* bias,
     const int num_sms = sm_count_current_device();
     const int tiles = X * ((Y + TILE_Y - 1) / TILE_Y);
     const int grid = tiles < num_sms ? tiles : num_sms;
-    static const bool uni = getenv("OCC_CONV_SINGLE_LANE") == nullptr;      // OCC_CONV_SINGLE_LANE=1: the lane-0-only loops
+    static const bool uni = getenv("OCC_CONV_SINGLE_LANE") == nullptr;      // OCC_CONV_SINGLE_LANE=1: the lane-0-only loops (EPI 0 only)
 #define OCC_CONV_LAUNCH(C, U)                                                                                          \
     do {                                                                                                               \
-        OCC_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<C, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));     \
-        conv3d_tc_kernel<C, U><<<grid, NUM_THREADS, smem, stream>>>(tmIn, tmW, bias, out, X, Y);                       \
+        OCC_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<C, U, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        conv3d_tc_kernel<C, U, EPI><<<grid, NUM_THREADS, smem, stream>>>(tmIn, tmW, bias, out, out_f32, X, Y);         \
     } while (0)
-    if (Cin == 16) { if (uni) OCC_CONV_LAUNCH(16, true); else OCC_CONV_LAUNCH(16, false); }
-    else           { if (uni) OCC_CONV_LAUNCH(32, true); else OCC_CONV_LAUNCH(32, false); }
+    if constexpr (EPI == 0) {
+        if (Cin == 16) { if (uni) OCC_CONV_LAUNCH(16, true); else OCC_CONV_LAUNCH(16, false); }
+        else           { if (uni) OCC_CONV_LAUNCH(32, true); else OCC_CONV_LAUNCH(32, false); }
+    } else {
+        if (Cin == 16) OCC_CONV_LAUNCH(16, true); else OCC_CONV_LAUNCH(32, true);
+    }
 #undef OCC_CONV_LAUNCH
     OCC_CUDA(cudaGetLastError());
     return 0;
+}
+}  // namespace
+
+int launch_conv3d_tc(const bf16* in, const bf16* w_tap_major, const float* bias, int X, int Y, int Z, int Cin,
+                     bf16* out, cudaStream_t stream)
+{
+    return launch_conv3d_tc_impl<0>(in, Cin, w_tap_major, bias, X, Y, Z, Cin, out, nullptr, stream);
+}
+
+// fp32-grade convolution on the tensor cores: split = [hi | lo] bf16 halves of the fp32 input ([nvox][2*Cin], launch_split_bf16),
+// w_hi / w_lo = bf16 split of the BN-folded fp32 weights ([27][32][Cin] each); out_f32 = relu(hi.W_hi + lo.W_hi + hi.W_lo + bias)
+// accumulated in fp32 over three passes of the same kernel (the lo.lo term, 2^-16 relative, is dropped)
+int launch_conv3d_tc_split(const bf16* split, const bf16* w_hi, const bf16* w_lo, const float* bias, int X, int Y, int Z, int Cin,
+                           float* out_f32, cudaStream_t stream)
+{
+    if (launch_conv3d_tc_impl<1>(split, 2 * Cin, w_hi, bias, X, Y, Z, Cin, nullptr, out_f32, stream)) return 1;
+    if (launch_conv3d_tc_impl<2>(split + Cin, 2 * Cin, w_hi, bias, X, Y, Z, Cin, nullptr, out_f32, stream)) return 1;
+    return launch_conv3d_tc_impl<3>(split, 2 * Cin, w_lo, bias, X, Y, Z, Cin, nullptr, out_f32, stream);
 }
 
 }  // namespace occ

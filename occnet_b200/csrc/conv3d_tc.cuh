@@ -10,6 +10,11 @@ namespace occ {
 int launch_conv3d_tc(const bf16* in, const bf16* w_tap_major, const float* bias, int X, int Y, int Z, int Cin,
                      bf16* out, cudaStream_t stream);
 
+// fp32 storage on the tensor cores: split = [hi | lo] bf16 halves of the fp32 input ([nvox][2*Cin]); w_hi / w_lo the bf16 split of
+// the folded weights; out_f32 [nvox][32] = relu(hi.W_hi + lo.W_hi + hi.W_lo + bias), three passes accumulated in fp32
+int launch_conv3d_tc_split(const bf16* split, const bf16* w_hi, const bf16* w_lo, const float* bias, int X, int Y, int Z, int Cin,
+                           float* out_f32, cudaStream_t stream);
+
 // vox bf16 [nvox][32]; w1cat bf16 [128][32] = [predicter.0 ; flow_predicter.0]; w2cat bf16 [32][128] block-diagonal
 // [predicter.2 | 0 ; 0 | flow_predicter.2 ; 0]; b1cat f32 [128]; b2cat f32 [ncls + 2]
 int launch_occ_head_tc(const bf16* vox, const bf16* w1cat, const bf16* w2cat, const float* b1cat, const float* b2cat,

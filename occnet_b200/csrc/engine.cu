@@ -81,6 +81,7 @@ struct occb200_engine {
     DevBuf l0_x_f32, l0_q_t;
     bool l0_ready = false;
     DevBuf conv_w[2], conv_b[2], conv_wh[2];
+    DevBuf conv_wh_hi[2], conv_wh_lo[2], vox_split;      // fp32 storage + tensor cores: bf16 hi / lo split of the folded conv weights, [hi | lo] voxel operand
     DevBuf sca_v_all_wh, sca_v_all_b, sca_value_all;     // value_proj of every layer, concatenated (tensor-core path)
     DevBuf hw1, hb1, hw2, hb2, fw1, fb1, fw2, fb2, head_w1h, head_w2h, head_b1c, head_b2c;
     // workspace
@@ -570,6 +571,21 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
         } else if (launch_bev_to_voxel<T>(q_f32, c.bev_h, c.bev_w, Z, mid, e->vox0.as<T>(), st)) return 2;
     }
     const bool conv_tc = sizeof(T) == 2 && c.use_tensor_cores && e->conv_wh[0].p && e->conv_wh[1].p && Z == 16;
+    // fp32 storage + tensor cores: both convolutions as three bf16-split passes accumulated in fp32 (OCC_CONV_F32_SIMT=1: CUDA cores)
+    static const bool conv_simt_env = getenv("OCC_CONV_F32_SIMT") != nullptr;
+    const bool conv_split = sizeof(T) == 4 && c.use_tensor_cores && !conv_simt_env && e->conv_wh_hi[0].p && e->conv_wh_lo[1].p &&
+                            e->vox_split.p && Z == 16 && (mid == 16 || mid == 32) && c.out_dim == 32;
+    if (conv_split) {
+        const int64_t nv = (int64_t)X * Y * Z;
+        ProfScope ps(e, st, CAT_CONV);
+        if (launch_split_bf16(e->vox0.as<float>(), mid, nullptr, 0, nv, e->vox_split.as<bf16>(), st)) return 2;
+        if (launch_conv3d_tc_split(e->vox_split.as<bf16>(), e->conv_wh_hi[0].as<bf16>(), e->conv_wh_lo[0].as<bf16>(), e->conv_b[0].as<float>(),
+                                   X, Y, Z, mid, e->vox1.as<float>(), st)) return 2;
+        if (launch_split_bf16(e->vox1.as<float>(), c.out_dim, nullptr, 0, nv, e->vox_split.as<bf16>(), st)) return 2;
+        if (launch_conv3d_tc_split(e->vox_split.as<bf16>(), e->conv_wh_hi[1].as<bf16>(), e->conv_wh_lo[1].as<bf16>(), e->conv_b[1].as<float>(),
+                                   X, Y, Z, c.out_dim, e->vox2.as<float>(), st)) return 2;
+        e->launches += 6;                                       // (+ the 2 counted below = 2 splits + 6 conv passes)
+    } else {
     {
         ProfScope ps(e, st, CAT_CONV);
         if (conv_tc) {
@@ -586,6 +602,7 @@ int forward_impl(occb200_engine* e, const float* const* feats, const float* prev
         } else if (launch_conv3d_simt<T>(e->vox1.as<T>(), e->conv_w[1].as<float>(), e->conv_b[1].as<float>(), X, Y, Z,
                                          c.out_dim, e->vox2.as<T>(), st)) return 2;
     }
+    }   // (!conv_split)
     HeadWeights hw{e->hw1.as<float>(), e->hb1.as<float>(), e->hw2.as<float>(), e->hb2.as<float>(),
                    e->fw1.as<float>(), e->fb1.as<float>(), e->fw2.as<float>(), e->fb2.as<float>(), c.num_classes};
     {
@@ -683,7 +700,8 @@ void occb200_engine_destroy(occb200_engine* e)
         for (DevBuf* b : all) b->release();
     }
     DevBuf* all[] = {&e->sca_sched, &e->rot_map, &e->split_ws, &e->tokens_split, &e->l0_x_f32, &e->l0_q_t, &e->pos_bf, &e->qc_f32, &e->qc_t, &e->qc_pos_t, &e->bev_queries, &e->pos, &e->pos_t32, &e->cams_embeds, &e->level_embeds, &e->conv_w[0], &e->conv_w[1],
-                     &e->conv_b[0], &e->conv_b[1], &e->conv_wh[0], &e->conv_wh[1], &e->sca_v_all_wh, &e->sca_v_all_b, &e->sca_value_all, &e->hw1, &e->hb1, &e->hw2, &e->hb2,
+                     &e->conv_b[0], &e->conv_b[1], &e->conv_wh[0], &e->conv_wh[1], &e->conv_wh_hi[0], &e->conv_wh_hi[1], &e->conv_wh_lo[0],
+                     &e->conv_wh_lo[1], &e->vox_split, &e->sca_v_all_wh, &e->sca_v_all_b, &e->sca_value_all, &e->hw1, &e->hb1, &e->hw2, &e->hb2,
                      &e->fw1, &e->fb1, &e->fw2, &e->fb2, &e->head_w1h, &e->head_w2h, &e->head_b1c, &e->head_b2c, &e->tokens, &e->sca_value, &e->q_f32, &e->q_t,
                      &e->q_pos_t, &e->q0_t, &e->prev_t, &e->tsa_value, &e->tsa_value_prev, &e->qproj, &e->attn_out,
                      &e->x_f32, &e->ffn_h, &e->vox0, &e->vox1, &e->vox2, &e->hits, &e->tap_layer, &e->tap_tsa,
@@ -878,6 +896,18 @@ int occb200_engine_finalize(occb200_engine* e)
                         wt[((size_t)t * od + co) * cin + ci] = wf[((size_t)t * cin + ci) * od + co];
             if (upload_bf16(e->conv_wh[i], wt.data(), wt.size())) return 2;
         }
+        if (tc32 && c.pillar_h == 16) {                       // same layout, split into bf16 hi + lo (3-pass fp32-grade convolution)
+            std::vector<float> hi((size_t)27 * od * cin), lo(hi.size());
+            for (int t = 0; t < 27; ++t)
+                for (int co = 0; co < od; ++co)
+                    for (int ci = 0; ci < cin; ++ci) {
+                        const float w = wf[((size_t)t * cin + ci) * od + co];
+                        const float h = __bfloat162float(__float2bfloat16(w));
+                        hi[((size_t)t * od + co) * cin + ci] = h;
+                        lo[((size_t)t * od + co) * cin + ci] = w - h;
+                    }
+            if (upload_bf16(e->conv_wh_hi[i], hi.data(), hi.size()) || upload_bf16(e->conv_wh_lo[i], lo.data(), lo.size())) return 2;
+        }
     }
     {
         GETP(w1, "transformer.predicter.0.weight", (size_t)2 * od * od);
@@ -925,6 +955,7 @@ int occb200_engine_finalize(occb200_engine* e)
     if (tc32) {
         const size_t kmax = (size_t)std::max(2 * C, F);
         if (e->split_ws.alloc((size_t)Nq * 2 * kmax * 2) || e->tokens_split.alloc(ntok * 2 * C * 2)) return 2;
+        if (c.pillar_h == 16 && e->vox_split.alloc(nvox * 2 * od * 2)) return 2;
     }
     e->host_params.clear();
     e->l0_ready = false;
