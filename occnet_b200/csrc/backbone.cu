@@ -3,10 +3,10 @@
 // bevformer_base_occ.py:48-66 puts in front of the hot path (caller: detectors/bevformer_occ.py:66-99; eval mode:
 // GridMask is the identity, BatchNorm uses running statistics).  SURVEY 8f rank 1 ("next").
 //
-// STATUS: first version, written after the round-1 GPU budget was spent -- builds for sm_100a, NOT yet run on a GPU;
-// nothing on the measured path calls it and its parity tests are opt-in (OCC_EXPERIMENTAL=1).  See
-// backbone_kernels.cu for the design (NHWC activations, explicit im2col, every convolution a GEMM on the validated
-// tcgen05 kernel or -- fp32 parity configuration -- the CUDA-core GEMM).
+// STATUS: validated on B200 in round 2 (tests/test_backbone_gpu.py); default feature extractor of the drop-in detector when it
+// is given images.  See backbone_kernels.cu / conv2d_tc.cu for the design (NHWC activations, BatchNorm folded, stride-1
+// convolutions on the TMA-im2col implicit-GEMM kernel, the others explicit im2col + the tcgen05 GEMM; fp32 parity
+// configuration: the CUDA-core GEMM).
 #include <cuda_runtime.h>
 
 #include <algorithm>

@@ -1,10 +1,11 @@
 // Layout / data-movement kernels of the image backbone + neck (ResNet-50 + FPN feeding the hot path, SURVEY 8f rank 1;
 // reference: detectors/bevformer_occ.py:66-99 with the mmdet modules configured in bevformer_base_occ.py:48-66).
 //
-// STATUS: first version, written after the round-1 GPU budget was spent -- compiled for sm_100a but NOT yet run on a
-// GPU.  Nothing on the measured hot path calls it; its parity tests are opt-in (OCC_EXPERIMENTAL=1).
+// STATUS: validated on B200 in round 2 (tests/test_backbone_gpu.py, 8 tests against the pinned backbone oracle); the bench's
+// `images_to_voxels` leg times it (profiles/README.md).  The stride-1 3x3 convolutions and the bottleneck's last 1x1 moved to the
+// TMA-im2col kernel conv2d_tc.cu; what is described here is the explicit-im2col path that the remaining convolutions still use.
 //
-// Design of this first version: activations are channels-last (NHWC); every convolution is a GEMM on the validated
+// Design of the explicit path: activations are channels-last (NHWC); every convolution is a GEMM on the validated
 // tcgen05 kernel (gemm_tc.cu; CUDA-core gemm_simt.cu in the fp32 parity configuration):
 //   1x1 stride 1          : the NHWC tensor IS the [pixels, Cin] operand
 //   3x3 / 7x7 / strided   : explicit im2col into a [pixels_out, K] operand (K = KH*KW*Cin zero-padded to 64)
