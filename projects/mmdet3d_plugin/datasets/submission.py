@@ -14,11 +14,8 @@ import numpy as np
 
 from .ray_metrics import generate_lidar_rays, process_one_sample
 
-SUBMISSION_META = {
-    'method': 'XXXXX (Your method name)', 'team': 'XXXXX (Your team name)', 'authors': 'XXXXX (Authors)',
-    'e-mail': 'XXXXX (Your email)', 'institution / company': 'XXXXXXXXXX (Your affiliation)',
-    'country / region': 'XXXXXXX (Your country/region)',
-}
+# header fields of the challenge file (same keys as the reference writer; the values are for the submitter to fill in)
+SUBMISSION_META = {'method': '', 'team': '', 'authors': '', 'e-mail': '', 'institution / company': '', 'country / region': ''}
 
 
 def format_results(occ_results, sample_tokens, lidar_origins, submission_prefix=None, meta=None, device='cuda:0'):
