@@ -168,3 +168,35 @@ def test_pack_transpose_swizzle_is_conflict_free_and_consistent():
     for p in range(64):
         pieces = sorted(addr(p, c8) * 2 // 16 for c8 in range(0, 64, 8))
         assert pieces == list(range(p * 8, p * 8 + 8))
+
+
+def test_chain_kernel_completion_protocol_never_publishes_an_incomplete_tile():
+    """gemm_chain.cu: an op whose rows feed the next op publishes tile completions WITHOUT waiting on its freshest stores: after
+    tile t the issuing lane waits until at most `groups(t)` of its bulk store groups are pending (cp.async.bulk.wait_group) and
+    publishes tile t-1; after the last tile it waits for everything and publishes the last one.  Model: 8 epilogue warps, bulk
+    groups complete in FIFO order per warp at random times; the consumer may load tile t once the counter reaches 8 * (t + 1)."""
+    rng = np.random.RandomState(1)
+    for trial in range(200):
+        n_tiles = int(rng.randint(1, 5))
+        groups_per_tile = [[int(rng.choice([0, 3, 4, 8])) for _ in range(n_tiles)] for _ in range(8)]   # 0: warp inactive for the tile
+        done_counter = 0
+        published_when = {}                                       # tile -> list of (warp, groups of that tile all complete?)
+        for w in range(8):
+            committed = []                                        # tile index of every committed group, in order
+            completed = 0                                         # groups completed so far (FIFO)
+            for t in range(n_tiles):
+                committed += [t] * groups_per_tile[w][t]
+                completed = min(len(committed), completed + int(rng.randint(0, 6)))     # some older groups finish meanwhile
+                if t > 0:
+                    pending_allowed = groups_per_tile[w][t]
+                    completed = max(completed, len(committed) - pending_allowed)          # wait_group(pending_allowed)
+                    ok = all(i < completed for i, tt in enumerate(committed) if tt <= t - 1)
+                    published_when.setdefault(t - 1, []).append(ok)
+                    done_counter += 1
+                if t == n_tiles - 1:
+                    completed = len(committed)                                            # wait_group 0
+                    published_when.setdefault(t, []).append(True)
+                    done_counter += 1
+        assert done_counter == 8 * n_tiles
+        for t in range(n_tiles):
+            assert len(published_when[t]) == 8 and all(published_when[t]), (trial, t, groups_per_tile)
